@@ -1,0 +1,89 @@
+"""ctypes binding of libgg_b200.so -- the only door between Python and the sm_100a kernels.
+
+PyTorch is used for device memory and streams only: every op allocates its outputs with torch,
+hands raw device pointers + the current CUDA stream to the C ABI (include/gg_b200.h) and raises
+RuntimeError with gg_last_error() on a non-zero return.  If the shared object is missing the import
+of any op fails loudly (no fallback path exists).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgg_b200.so")
+
+GG_F32, GG_F16, GG_BF16 = 0, 1, 2
+PAD_MODES = {"zeros": 0, "border": 1, "reflection": 2}
+
+_c = ctypes
+_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/gg_b200.h
+SIGNATURES = {
+    "gg_version": (_I, []),
+    "gg_last_error": (_c.c_char_p, []),
+    "gg_sm_count": (_I, []),
+    "gg_fused_bias_act": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _L, _L, _L, _P]),
+    "gg_noise_bias_act": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _L, _L, _L, _P]),
+    "gg_bias_act_backward_workspace": (_L, [_L, _L, _L]),
+    "gg_bias_act_backward": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _L, _L, _L, _P]),
+    "gg_upfirdn2d": (_I, [_P, _P, _P, _I, _L] + [_I] * 12 + [_P]),
+    "gg_blur_noise_bias_act": (_I, [_P] * 7 + [_I, _L, _L] + [_I] * 9 + [_F, _F, _P]),
+}
+
+_dll = None
+
+
+def load():
+    """Load (once) and type the shared library.  Raises RuntimeError if it has not been built."""
+    global _dll
+    if _dll is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libgg_b200.so is missing (%s): build it with `python -m gangealing_b200.build` "
+                "(there is no CPU/PyTorch fallback for these ops)" % LIB_PATH)
+        dll = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(dll, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _dll = dll
+    return _dll
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().gg_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
+
+
+def dtype_code(t):
+    d = t.dtype
+    if d == torch.float32:
+        return GG_F32
+    if d == torch.float16:
+        return GG_F16
+    if d == torch.bfloat16:
+        return GG_BF16
+    raise RuntimeError("gangealing_b200: dtype %s is not supported (float32/float16/bfloat16)" % d)
+
+
+def require_cuda(*tensors):
+    """Mirror of the reference's CHECK_CUDA (models/stylegan2/op/upfirdn2d.cpp:8): CUDA tensors only."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gangealing_b200 ops run on CUDA tensors only (got a %s tensor); "
+                               "the CPU restatement lives in oracle/ and is test infrastructure" % t.device.type)
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def sm_count():
+    return load().gg_sm_count()
