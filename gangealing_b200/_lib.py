@@ -30,6 +30,15 @@ SIGNATURES = {
     "gg_bias_act_backward": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _L, _L, _L, _P]),
     "gg_upfirdn2d": (_I, [_P, _P, _P, _I, _L] + [_I] * 12 + [_P]),
     "gg_blur_noise_bias_act": (_I, [_P] * 7 + [_I, _L, _L] + [_I] * 9 + [_F, _F, _P]),
+    "gg_mipmap_pyramid_elems": (_L, [_L, _I, _I, _I]),
+    "gg_mipmap_build": (_I, [_P, _P, _I, _L, _I, _I, _I, _P]),
+    "gg_mipmap_build_backward": (_I, [_P, _P, _L, _I, _I, _I, _P]),
+    "gg_mipmap_warp_forward": (_I, [_P] * 5 + [_I, _L] + [_I] * 6 + [_F, _F, _I, _P]),
+    "gg_splat2d_workspace": (_L, [_L, _I, _I, _I]),
+    "gg_splat2d_forward": (_I, [_P] * 6 + [_L, _L, _I, _I, _I, _I, _P]),
+    "gg_flow_compose_forward": (_I, [_P] * 7 + [_L, _I, _I, _I, _P]),
+    "gg_flow_compose_backward": (_I, [_P] * 10 + [_L, _I, _I, _I, _P]),
+    "gg_mipmap_warp_backward": (_I, [_P] * 7 + [_I, _L] + [_I] * 6 + [_F, _F, _I, _P]),
 }
 
 _dll = None

@@ -16,6 +16,8 @@
 //    Algorithmic bytes/launch = s*M*(Hin*Win + Hout*Wout) [+ s*N*Hout*Wout noise + 4*(C+1+16)].
 //  * upfirdn2d_generic_kernel: any up/down/pad/filter size (RGB skip up x2, its backward down x2,
 //    5x5 test filters ...): one thread per output, polyphase tap walk, fp32 accumulate.
+#include <utility>
+
 #include "common.cuh"
 
 namespace gg {
@@ -31,16 +33,28 @@ struct GenericParams {
   int pad_x0, pad_y0;
 };
 
+struct Epilogue {          // optional fused tail: lrelu(row_scale*t + nw*noise + bias) * scale
+  const void* noise;       // (N, out_h, out_w), element type of the tensor, or null
+  const float* noise_weight;
+  const float* bias;       // (C)
+  const float* row_scale;  // (N*C)
+  int C;
+  int act;
+  float alpha, scale;
+};
+
 __device__ __forceinline__ int floordiv(int a, int b) {  // b > 0
   int q = a / b;
   return (q * b > a) ? q - 1 : q;
 }
 __device__ __forceinline__ int ceildiv_s(int a, int b) { return -floordiv(-a, b); }
 
-template <typename T>
+template <typename T, bool FUSED>
 __global__ void __launch_bounds__(256)
 upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __restrict__ taps,
-                         GenericParams p, int64_t total) {
+                         GenericParams p, Epilogue ep, int64_t total) {
+  float nw = 0.f;
+  if (FUSED) nw = ep.noise ? (ep.noise_weight ? __ldg(ep.noise_weight) : 1.f) : 0.f;
   // out[m, oy, ox] = sum_{ky,kx} U[oy*dy + ky, ox*dx + kx] * taps[kh-1-ky][kw-1-kx]
   // U = zero-inserted, padded input: U[y, x] = in[(y-pad_y0)/up_y, (x-pad_x0)/up_x] when divisible & in range.
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -66,6 +80,14 @@ upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ in, const fl
         acc = fmaf(Cvt<T>::to_f(irow[ix]), __ldg(trow + (p.kw - 1 - kx)), acc);
       }
     }
+    if (FUSED) {
+      const int64_t n = m / ep.C;
+      const int c = static_cast<int>(m - n * ep.C);
+      float t = acc * (ep.row_scale ? __ldg(ep.row_scale + m) : 1.f) + (ep.bias ? __ldg(ep.bias + c) : 0.f);
+      if (ep.noise)
+        t = fmaf(nw, Cvt<T>::to_f(static_cast<const T*>(ep.noise)[(n * p.out_h + oy) * static_cast<int64_t>(p.out_w) + ox]), t);
+      acc = t * ((ep.act == 3 && t < 0.f) ? ep.alpha * ep.scale : ep.scale);
+    }
     out[idx] = Cvt<T>::from_f(acc);
   }
 }
@@ -76,15 +98,20 @@ upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ in, const fl
 constexpr int kBandThreads = 256;
 constexpr int kBandWarps = kBandThreads / 32;
 constexpr int kStages = 3;
-constexpr int kRS = 8;  // output rows per warp task (register window slides over kRS + 3 input rows)
+constexpr int kRS = 8;   // output rows per lane (the register window slides over kRS + 3 input rows)
+constexpr int kCO = 4;   // adjacent output columns per lane (one 16-byte store for fp32)
+constexpr int kFrontBytes = 16;  // guard in front of every stage so column -1..-3 of the first staged row is addressable
 
 struct BandParams {
   int64_t planes;        // M = N*C
   int in_h, in_w, out_h, out_w;
   int pad_x0, pad_y0;
-  int band_rows;         // R: output rows per work item (multiple of kRS)
-  int bands;             // ceil(out_h / R)
-  int stage_elems;       // shared-memory elements per stage (>= (R+3)*in_w + 2*16/sizeof(T))
+  int band_rows;         // R: output rows per work item
+  int bands;             // ceil(out_h / R); when 1, an item may span several whole planes
+  int planes_per_item;   // P (1 unless bands == 1)
+  int stage_elems;       // shared-memory elements per stage
+  int lx_log2;           // lanes across a strip = 1 << lx_log2 (strip = 4*lanes columns)
+  int vec_io;            // 1: out (and noise) rows are 16-byte aligned -> vector store / load
   // fused epilogue
   int C;                 // channels (plane m -> n = m / C, c = m % C)
   int act;               // 1 linear, 3 lrelu
@@ -96,25 +123,42 @@ struct Span {            // contiguous input span of one work item
   const T* src;          // 16-byte aligned start
   uint32_t bytes;        // multiple of 16 (0: band sees only padding)
   int shift;             // elements between src and the first needed element
-  int iy_lo;             // first staged input row
+  int iy_lo;             // first staged input row (of the item's first plane)
+  int64_t m0;            // first plane
+  int n_planes;          // planes in this item
+  int n_rows_staged;     // staged input rows (single-plane items)
+  int oy0, rows;         // output rows of the band
 };
 
 template <typename T>
 __device__ __forceinline__ Span<T> item_span(const T* in, const BandParams& p, int64_t item) {
   Span<T> s;
-  const int64_t m = item / p.bands;
-  const int band = static_cast<int>(item - m * p.bands);
-  const int oy0 = band * p.band_rows;
-  const int rows = min(p.band_rows, p.out_h - oy0);
-  const int lo = max(oy0 - p.pad_y0, 0);
-  const int hi = min(oy0 + rows - 1 + 3 - p.pad_y0, p.in_h - 1);
+  if (p.bands == 1) {
+    s.m0 = item * p.planes_per_item;
+    s.n_planes = static_cast<int>(min(static_cast<int64_t>(p.planes_per_item), p.planes - s.m0));
+    s.oy0 = 0;
+    s.rows = p.out_h;
+  } else {
+    s.m0 = item / p.bands;
+    s.n_planes = 1;
+    s.oy0 = static_cast<int>(item - s.m0 * p.bands) * p.band_rows;
+    s.rows = min(p.band_rows, p.out_h - s.oy0);
+  }
+  int lo, hi;
+  if (s.n_planes > 1) {  // whole planes, back to back
+    lo = 0; hi = p.in_h - 1;
+  } else {
+    lo = max(s.oy0 - p.pad_y0, 0);
+    hi = min(s.oy0 + s.rows - 1 + 3 - p.pad_y0, p.in_h - 1);
+  }
   s.iy_lo = lo;
+  s.n_rows_staged = hi - lo + 1;
   if (hi < lo) {
     s.src = in; s.bytes = 0; s.shift = 0;
     return s;
   }
-  const T* first = in + (m * p.in_h + lo) * static_cast<int64_t>(p.in_w);
-  const T* last = in + (m * p.in_h + hi + 1) * static_cast<int64_t>(p.in_w);  // one past
+  const T* first = in + (s.m0 * p.in_h + lo) * static_cast<int64_t>(p.in_w);
+  const T* last = in + ((s.m0 + s.n_planes - 1) * p.in_h + hi + 1) * static_cast<int64_t>(p.in_w);  // one past
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(first) & ~static_cast<uintptr_t>(15);
   const uintptr_t a1 = (reinterpret_cast<uintptr_t>(last) + 15) & ~static_cast<uintptr_t>(15);
   s.src = reinterpret_cast<const T*>(a0);
@@ -123,13 +167,237 @@ __device__ __forceinline__ Span<T> item_span(const T* in, const BandParams& p, i
   return s;
 }
 
-// CO = output columns per lane (interleaved by 32: conflict-free shared-memory reads at any shift)
-template <typename T, int CO, bool FUSED>
+template <typename T> struct Vec4 { T v[4]; };
+
+// One lane: 4 adjacent output columns x up to kRS output rows of one plane, register window sliding down.
+// SEP: the filter is an outer product u (rows) x v (columns): horizontal pass once per input row, vertical
+// pass over a 4-row window of horizontal results (8 FMA/output instead of 16).
+template <typename T, bool SEP, bool FUSED>
+__device__ __forceinline__ void lane_strip(T* __restrict__ out_plane, const T* __restrict__ tile_plane,
+                                           const T* __restrict__ noise_plane, const BandParams& p,
+                                           const float (&kf)[4][4], const float (&ku)[4], const float (&kv)[4],
+                                           int oys, int nrow, int x0, int iy_lo, float rs, float bc, float nw) {
+  // tile_plane points at staged row iy_lo of this plane; output rows [oys, oys + nrow), columns [x0, x0 + 4)
+  const int colbase = x0 - p.pad_x0;
+  int cidx[kCO + 3];
+  uint32_t cmask[kCO + 3];
+#pragma unroll
+  for (int i = 0; i < kCO + 3; ++i) {
+    const int c = colbase + i;
+    const bool ok = (c >= 0) && (c < p.in_w);
+    cidx[i] = min(max(c, 0), p.in_w - 1);
+    cmask[i] = ok ? 0xffffffffu : 0u;
+  }
+  const int iys = oys - p.pad_y0;
+
+  // separable path: all noise rows of the strip are fetched up front (latency fully hidden behind the
+  // window warm-up); the 16-tap path needs its registers for the raw window and loads them at use
+  Vec4<T> nz[SEP ? kRS : 1];
+  if (SEP && FUSED && noise_plane) {
+#pragma unroll
+    for (int r = 0; r < kRS; ++r) {
+      if (r < nrow) {
+        const T* np_ = noise_plane + static_cast<int64_t>(oys + r) * p.out_w + x0;
+        if (p.vec_io) {
+          nz[r] = *reinterpret_cast<const Vec4<T>*>(np_);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kCO; ++j) nz[r].v[j] = (x0 + j < p.out_w) ? np_[j] : Cvt<T>::from_f(0.f);
+        }
+      }
+    }
+  }
+
+  float win[4][SEP ? kCO : kCO + 3];
+#pragma unroll
+  for (int r = 0; r < kRS + 3; ++r) {
+    if (r < nrow + 3) {
+      const int iy = iys + r;
+      float raw[kCO + 3];
+      if (iy >= 0 && iy < p.in_h) {
+        const T* trow = tile_plane + static_cast<int64_t>(iy - iy_lo) * p.in_w;
+#pragma unroll
+        for (int i = 0; i < kCO + 3; ++i)
+          raw[i] = __uint_as_float(__float_as_uint(Cvt<T>::to_f(trow[cidx[i]])) & cmask[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kCO + 3; ++i) raw[i] = 0.f;
+      }
+      if (SEP) {
+#pragma unroll
+        for (int j = 0; j < kCO; ++j)
+          win[r & 3][j] = fmaf(kv[3], raw[j + 3], fmaf(kv[2], raw[j + 2], fmaf(kv[1], raw[j + 1], kv[0] * raw[j])));
+      } else {
+#pragma unroll
+        for (int i = 0; i < kCO + 3; ++i) win[r & 3][i] = raw[i];
+      }
+      if (r >= 3) {
+        const int ro = r - 3;
+        float acc[kCO];
+#pragma unroll
+        for (int j = 0; j < kCO; ++j) {
+          if (SEP) {
+            acc[j] = fmaf(ku[3], win[(ro + 3) & 3][j],
+                          fmaf(ku[2], win[(ro + 2) & 3][j], fmaf(ku[1], win[(ro + 1) & 3][j], ku[0] * win[ro & 3][j])));
+          } else {
+            float a_ = 0.f;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) a_ = fmaf(win[(ro + a) & 3][j + b], kf[a][b], a_);
+            acc[j] = a_;
+          }
+          if (FUSED) {
+            float t = fmaf(acc[j], rs, bc);
+            if (noise_plane) {
+              const float nv = SEP ? Cvt<T>::to_f(nz[SEP ? ro : 0].v[j])
+                                   : ((x0 + j < p.out_w)
+                                          ? Cvt<T>::to_f(noise_plane[static_cast<int64_t>(oys + ro) * p.out_w + x0 + j])
+                                          : 0.f);
+              t = fmaf(nw, nv, t);
+            }
+            const float g = (p.act == 3 && t < 0.f) ? p.alpha * p.scale : p.scale;
+            acc[j] = t * g;
+          }
+        }
+        T* op = out_plane + static_cast<int64_t>(oys + ro) * p.out_w + x0;
+        if (p.vec_io) {
+          Vec4<T> o;
+#pragma unroll
+          for (int j = 0; j < kCO; ++j) o.v[j] = Cvt<T>::from_f(acc[j]);
+          *reinterpret_cast<Vec4<T>*>(op) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < kCO; ++j)
+            if (x0 + j < p.out_w) op[j] = Cvt<T>::from_f(acc[j]);
+        }
+      }
+    }
+  }
+}
+
+// fp32 + separable filter fast path.  The stage holds the span as one flat array, so element (row, col) sits at
+// flat position pos = row*in_w + col + const, whose 16-byte alignment rotates from row to row (in_w is odd on
+// the hot path).  Each lane reads the 16-byte-aligned quads covering its 7 inputs (LDS.128, consecutive lanes ->
+// consecutive quads: conflict-free).  Which registers feed the horizontal pass depends on pos mod 4, which is
+// WARP-UNIFORM and, given the alignment S0 of the strip's first row and IW4 = in_w mod 4, a compile-time
+// constant per unrolled row: the kernel is instantiated per IW4 and branches once per task on S0, so the
+// inner loop has no shuffles, selects or per-value address arithmetic.
+// Out-of-range columns are handled by folding a 0/1 mask into per-lane horizontal weights.
+template <int IW4, int S0, bool FUSED, bool VEC>
+struct StripF32 {
+  float* __restrict__ out_ptr;        // &out[plane][oys][x0]
+  const float* __restrict__ stage;
+  const BandParams& p;
+  const float (&ku)[4];
+  float wgt[kCO][4];
+  float4 nz[kRS];
+  float hw[4][kCO];
+  int pos0, iys, nrow, x0;
+  float rs, bc, nw, gpos, gneg;
+  bool has_noise;
+
+  // Straight-line per-row step: no data-dependent branches.  Rows outside the image (zero padding) load from a
+  // safe aligned address and are zeroed by selects; rows past the strip's last output only feed outputs that
+  // are never stored.
+  template <int R>
+  __device__ __forceinline__ void step() {
+    const int iy = iys + R;
+    const bool rv = (iy >= 0) && (iy < p.in_h);
+    constexpr int SH = (S0 + R * IW4) & 3;       // alignment of this row's first input (compile-time)
+    const float* a = stage + (pos0 + R * p.in_w - SH);
+    a = rv ? a : stage;
+    const float4* qp = reinterpret_cast<const float4*>(a);
+    const float4 q0 = qp[0], q1 = qp[1];
+    float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (SH >= 2) q2 = qp[2];                     // inputs SH .. SH+6 reach the third quad only when SH >= 2
+    const float Q[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+    for (int j = 0; j < kCO; ++j) {
+      const float h = fmaf(wgt[j][3], Q[SH + j + 3],
+                           fmaf(wgt[j][2], Q[SH + j + 2], fmaf(wgt[j][1], Q[SH + j + 1], wgt[j][0] * Q[SH + j])));
+      hw[R & 3][j] = rv ? h : 0.f;
+    }
+    if (R >= 3) {
+      constexpr int RO = R >= 3 ? R - 3 : 0;
+      float acc[kCO];
+#pragma unroll
+      for (int j = 0; j < kCO; ++j) {
+        acc[j] = fmaf(ku[3], hw[(RO + 3) & 3][j],
+                      fmaf(ku[2], hw[(RO + 2) & 3][j], fmaf(ku[1], hw[(RO + 1) & 3][j], ku[0] * hw[RO & 3][j])));
+        if (FUSED) {
+          float t = fmaf(acc[j], rs, bc);
+          if (has_noise) {
+            const float4 nv4 = nz[RO < kRS ? RO : 0];
+            const float nv = j == 0 ? nv4.x : (j == 1 ? nv4.y : (j == 2 ? nv4.z : nv4.w));
+            t = fmaf(nw, nv, t);
+          }
+          acc[j] = t * (t < 0.f ? gneg : gpos);
+        }
+      }
+      if (RO < nrow) {
+        float* op = out_ptr + static_cast<int64_t>(RO) * p.out_w;
+        if (VEC) {
+          *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kCO; ++j)
+            if (x0 + j < p.out_w) op[j] = acc[j];
+        }
+      }
+    }
+  }
+
+  template <int... Rs>
+  __device__ __forceinline__ void run(std::integer_sequence<int, Rs...>) {
+    (step<Rs>(), ...);
+  }
+};
+
+template <int IW4, int S0, bool FUSED, bool VEC>
+__device__ __forceinline__ void lane_strip_f32(float* __restrict__ out_plane, const float* __restrict__ stage,
+                                               int pos0, const float* __restrict__ noise_plane, const BandParams& p,
+                                               const float (&ku)[4], const float (&kv)[4], int oys, int nrow, int x0,
+                                               float rs, float bc, float nw) {
+  // pos0: flat position (elements from the 16-byte-aligned `stage`) of input (row oys - pad_y0, column x0 - pad_x0)
+  StripF32<IW4, S0, FUSED, VEC> st{out_plane + static_cast<int64_t>(oys) * p.out_w + x0, stage, p, ku};
+  st.pos0 = pos0; st.iys = oys - p.pad_y0; st.nrow = nrow; st.x0 = x0;
+  st.rs = rs; st.bc = bc; st.nw = nw; st.has_noise = FUSED && noise_plane != nullptr;
+  st.gpos = p.scale; st.gneg = (p.act == 3) ? p.alpha * p.scale : p.scale;
+  const int colbase = x0 - p.pad_x0;
+#pragma unroll
+  for (int j = 0; j < kCO; ++j)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = colbase + j + b;
+      st.wgt[j][b] = (c >= 0 && c < p.in_w) ? kv[b] : 0.f;
+    }
+  if (FUSED && noise_plane) {
+#pragma unroll
+    for (int r = 0; r < kRS; ++r) {
+      st.nz[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrow) {
+        const float* np_ = noise_plane + static_cast<int64_t>(oys + r) * p.out_w + x0;
+        if (VEC) {
+          st.nz[r] = __ldg(reinterpret_cast<const float4*>(np_));
+        } else {
+          if (x0 + 0 < p.out_w) st.nz[r].x = __ldg(np_ + 0);
+          if (x0 + 1 < p.out_w) st.nz[r].y = __ldg(np_ + 1);
+          if (x0 + 2 < p.out_w) st.nz[r].z = __ldg(np_ + 2);
+          if (x0 + 3 < p.out_w) st.nz[r].w = __ldg(np_ + 3);
+        }
+      }
+    }
+  }
+  st.run(std::make_integer_sequence<int, kRS + 3>{});
+}
+
+template <typename T, int IW4, bool FUSED>
 __global__ void __launch_bounds__(kBandThreads, 2)
 fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __restrict__ filt, int kh,
                  int kw, const T* __restrict__ noise, const float* __restrict__ noise_weight,
-                 const float* __restrict__ bias, const float* __restrict__ row_scale, BandParams p,
-                 int64_t n_items) {
+                 const float* __restrict__ bias, const float* __restrict__ row_scale,
+                 const __grid_constant__ BandParams p, int64_t n_items) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[kStages];
   T* stage_base = reinterpret_cast<T*>(smem_raw);
@@ -143,19 +411,8 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
   }
   __syncthreads();
 
-  // flipped 4x4 taps in registers: kf[a][b] multiplies input (oy + a - pad_y0, ox + b - pad_x0)
-  float kf[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      kf[a][b] = (a < kh && b < kw) ? __ldg(filt + (kh - 1 - a) * kw + (kw - 1 - b)) : 0.f;  // flipped: true convolution
-
-  float nw = 0.f;
-  if (FUSED) nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
-
   const int64_t stride = gridDim.x;
-  // prologue: fill kStages-1 stages
+  // prologue: fill kStages-1 stages (issued before the tap set-up below so the copies fly meanwhile)
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
@@ -164,13 +421,71 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
         const Span<T> sp = item_span(in, p, it);
         if (sp.bytes) {
           mbar_expect_tx(&full_bar[s], sp.bytes);
-          tma_bulk_g2s(stage_base + static_cast<int64_t>(s) * p.stage_elems, sp.src, sp.bytes, &full_bar[s]);
+          tma_bulk_g2s(stage_base + static_cast<int64_t>(s) * p.stage_elems + kFrontBytes / sizeof(T), sp.src, sp.bytes,
+                       &full_bar[s]);
         }
       }
     }
   }
 
-  const int strips_x = (p.out_w + 32 * CO - 1) / (32 * CO);
+  // flipped 4x4 taps in registers: kf[a][b] multiplies input (oy + a - pad_y0, ox + b - pad_x0)
+  float kf[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      kf[a][b] = (a < kh && b < kw) ? __ldg(filt + (kh - 1 - a) * kw + (kw - 1 - b)) : 0.f;  // flipped: true convolution
+  // rank-1 test: kf == ku (x) kv within 1e-6 of the largest tap -> separable fast path (every Blur in
+  // GANgealing: [1,3,3,1] (x) [1,3,3,1], exactly representable)
+  float ku[4], kv[4];
+  bool sep;
+  {
+    int a0 = 0, b0 = 0;
+    float big = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (fabsf(kf[a][b]) > big) { big = fabsf(kf[a][b]); a0 = a; b0 = b; }
+    float piv = 1.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (a == a0 && b == b0) piv = kf[a][b];
+    const float inv = big > 0.f ? 1.f / piv : 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float col = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) if (b == b0) col = kf[a][b];
+      ku[a] = col * inv;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      float row = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) if (a == a0) row = kf[a][b];
+      kv[b] = row;
+    }
+    float dev = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dev = fmaxf(dev, fabsf(kf[a][b] - ku[a] * kv[b]));
+    sep = dev <= 1e-6f * big;
+  }
+
+  float nw = 0.f;
+  if (FUSED) nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
+
+  // strip geometry: `full_x` strips of lx lanes x 4 columns, plus one narrower tail strip whose lanes
+  // are folded down the rows instead (so 129- or 65-wide outputs do not pay for a second full strip)
+  const int lx_main = 1 << p.lx_log2;
+  const int full_x = p.out_w / (lx_main * kCO);
+  const int tail_w = p.out_w - full_x * lx_main * kCO;
+  int lt_log2 = 0;
+  while ((1 << lt_log2) * kCO < tail_w) ++lt_log2;
 
   uint32_t phase_bits = 0;  // bit s: parity the next wait on stage s must observe
   int k = 0;                // local iteration counter
@@ -184,97 +499,96 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
         const Span<T> sp = item_span(in, p, nxt);
         if (sp.bytes) {
           mbar_expect_tx(&full_bar[ns], sp.bytes);
-          tma_bulk_g2s(stage_base + static_cast<int64_t>(ns) * p.stage_elems, sp.src, sp.bytes, &full_bar[ns]);
+          tma_bulk_g2s(stage_base + static_cast<int64_t>(ns) * p.stage_elems + kFrontBytes / sizeof(T), sp.src, sp.bytes,
+                       &full_bar[ns]);
         }
       }
     }
     const Span<T> sp = item_span(in, p, item);
-    const int64_t m = item / p.bands;
-    const int band = static_cast<int>(item - m * p.bands);
-    const int oy0 = band * p.band_rows;
-    const int rows = min(p.band_rows, p.out_h - oy0);
     if (sp.bytes) {  // a padding-only band issues no transfer, so its stage's phase does not advance
       mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
       phase_bits ^= 1u << stage;
     }
-    const T* tile = stage_base + static_cast<int64_t>(stage) * p.stage_elems + sp.shift;
-
-    float rs = 1.f, bc = 0.f;
-    int64_t n = 0;
-    if (FUSED) {
-      n = m / p.C;
-      const int c = static_cast<int>(m - n * p.C);
-      if (row_scale) rs = __ldg(row_scale + m);
-      if (bias) bc = __ldg(bias + c);
+    T* stage_ptr = stage_base + static_cast<int64_t>(stage) * p.stage_elems;   // 16-byte aligned
+    const int tile_off = static_cast<int>(kFrontBytes / sizeof(T)) + sp.shift;     // staged row iy_lo, column 0
+    const T* tile = stage_ptr + tile_off;
+    if (sp.bytes) {
+      // The aligned superset drags in up to 3 foreign elements on either side of the span; zero-weight taps of
+      // edge lanes touch them (mask-folded weights), so make them finite zeros.  (Visible after the barrier.)
+      const int span_elems = static_cast<int>((sp.n_planes > 1 ? static_cast<int64_t>(sp.n_planes) * p.in_h
+                                                                : static_cast<int64_t>(sp.n_rows_staged)) * p.in_w);
+      if (tid < 3) stage_ptr[tile_off - 1 - tid] = Cvt<T>::from_f(0.f);
+      else if (tid < 6) stage_ptr[tile_off + span_elems + (tid - 3)] = Cvt<T>::from_f(0.f);
     }
+    __syncthreads();
 
-    const int strips_y = (rows + kRS - 1) / kRS;
-    const int n_tasks = strips_x * strips_y;
+    const int sy_main = (sp.rows + (32 >> p.lx_log2) * kRS - 1) / ((32 >> p.lx_log2) * kRS);
+    const int main_tasks = full_x * sy_main;
+    const int tail_tasks = tail_w > 0 ? (sp.rows + (32 >> lt_log2) * kRS - 1) / ((32 >> lt_log2) * kRS) : 0;
+    const int tasks_per_plane = main_tasks + tail_tasks;
+    const int n_tasks = tasks_per_plane * sp.n_planes;
     for (int task = warp; task < n_tasks; task += kBandWarps) {
-      const int sy = task / strips_x;
-      const int sx = task - sy * strips_x;
-      const int oys = oy0 + sy * kRS;                 // first output row of the strip
-      const int nrow = min(kRS, oy0 + rows - oys);    // valid output rows in the strip
-      const int iys = oys - p.pad_y0;                 // input row feeding tap row a = 0 of output oys
-
-      int col[CO];        // tile column of tap b = 0
-      unsigned msk[CO];   // bit b: tap column valid
-      bool cok[CO];
-#pragma unroll
-      for (int j = 0; j < CO; ++j) {
-        const int ox = sx * 32 * CO + lane + 32 * j;
-        cok[j] = ox < p.out_w;
-        col[j] = ox - p.pad_x0;
-        unsigned mk = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int ix = col[j] + b;
-          if (cok[j] && ix >= 0 && ix < p.in_w) mk |= 1u << b;
-        }
-        msk[j] = mk;
+      const int pl = task / tasks_per_plane;
+      const int rem = task - pl * tasks_per_plane;
+      int sy, xs, lg;  // strip row, first column of the strip, log2(lanes across)
+      if (rem < main_tasks) {
+        sy = rem / full_x;
+        xs = (rem - sy * full_x) * lx_main * kCO;
+        lg = p.lx_log2;
+      } else {
+        sy = rem - main_tasks;
+        xs = full_x * lx_main * kCO;
+        lg = lt_log2;
       }
-
-      float win[4][CO][4];
-#pragma unroll
-      for (int r = 0; r < kRS + 3; ++r) {
-        // load input row iys + r into window slot r & 3
-        const int iy = iys + r;
-        const bool row_ok = (iy >= 0) && (iy < p.in_h) && (r < nrow + 3);
-        const T* trow = tile + static_cast<int64_t>(iy - sp.iy_lo) * p.in_w;
-#pragma unroll
-        for (int j = 0; j < CO; ++j)
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            win[r & 3][j][b] = (row_ok && ((msk[j] >> b) & 1u)) ? Cvt<T>::to_f(trow[col[j] + b]) : 0.f;
-        if (r >= 3) {
-          const int ro = r - 3;  // output row within the strip
-          if (ro < nrow) {
-            const int oy = oys + ro;
-            T* orow = out + (m * p.out_h + oy) * static_cast<int64_t>(p.out_w);
-            const T* nrowp = nullptr;
-            if (FUSED && noise) nrowp = noise + (n * p.out_h + oy) * static_cast<int64_t>(p.out_w);
-#pragma unroll
-            for (int j = 0; j < CO; ++j) {
-              float acc = 0.f;
-#pragma unroll
-              for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc = fmaf(win[(ro + a) & 3][j][b], kf[a][b], acc);
-              if (cok[j]) {
-                const int ox = sx * 32 * CO + lane + 32 * j;
-                if (FUSED) {
-                  float t = acc * rs;
-                  if (nrowp) t = t + nw * Cvt<T>::to_f(nrowp[ox]);
-                  t += bc;
-                  if (p.act == 3) t = t > 0.f ? t : t * p.alpha;
-                  acc = t * p.scale;
-                }
-                orow[ox] = Cvt<T>::from_f(acc);
-              }
+      const int lane_x = lane & ((1 << lg) - 1);
+      const int lane_y = lane >> lg;
+      const int64_t m = sp.m0 + pl;
+      const int oys = sp.oy0 + (sy * (32 >> lg) + lane_y) * kRS;
+      const int nrow = min(kRS, sp.oy0 + sp.rows - oys);
+      const int x0 = xs + lane_x * kCO;
+      if (nrow <= 0 || x0 >= p.out_w) continue;
+      float rs = 1.f, bc = 0.f;
+      const T* noise_plane = nullptr;
+      if (FUSED) {
+        const int64_t n = m / p.C;
+        const int c = static_cast<int>(m - n * p.C);
+        if (row_scale) rs = __ldg(row_scale + m);
+        if (bias) bc = __ldg(bias + c);
+        if (noise) noise_plane = noise + n * p.out_h * static_cast<int64_t>(p.out_w);
+      }
+      T* out_plane = out + m * p.out_h * static_cast<int64_t>(p.out_w);
+      const T* tile_plane = tile + static_cast<int64_t>(pl) * p.in_h * p.in_w;
+      if constexpr (sizeof(T) == 4 && IW4 >= 0) {
+        if (sep) {
+          const int pos0 = tile_off + (pl * p.in_h + (oys - p.pad_y0 - sp.iy_lo)) * p.in_w + (x0 - p.pad_x0);
+#define GG_STRIP(S0_, V_)                                                                                    \
+  lane_strip_f32<IW4, S0_, FUSED, V_>(reinterpret_cast<float*>(out_plane),                                      \
+                                      reinterpret_cast<const float*>(stage_ptr), pos0,                          \
+                                      reinterpret_cast<const float*>(noise_plane), p, ku, kv, oys, nrow, x0, rs, \
+                                      bc, nw)
+          if (p.vec_io) {
+            switch (pos0 & 3) {   // warp-uniform: lanes differ by multiples of 4 columns / 8 rows
+              case 0: GG_STRIP(0, true); break;
+              case 1: GG_STRIP(1, true); break;
+              case 2: GG_STRIP(2, true); break;
+              default: GG_STRIP(3, true); break;
+            }
+          } else {
+            switch (pos0 & 3) {
+              case 0: GG_STRIP(0, false); break;
+              case 1: GG_STRIP(1, false); break;
+              case 2: GG_STRIP(2, false); break;
+              default: GG_STRIP(3, false); break;
             }
           }
+#undef GG_STRIP
+          continue;
         }
       }
+      if (sep)
+        lane_strip<T, true, FUSED>(out_plane, tile_plane, noise_plane, p, kf, ku, kv, oys, nrow, x0, sp.iy_lo, rs, bc, nw);
+      else
+        lane_strip<T, false, FUSED>(out_plane, tile_plane, noise_plane, p, kf, ku, kv, oys, nrow, x0, sp.iy_lo, rs, bc, nw);
     }
     __syncthreads();  // every warp is done with `stage` before it is refilled next iteration
   }
@@ -282,58 +596,78 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
 
 inline int dtype_size(int dtype) { return dtype == GG_F32 ? 4 : 2; }
 
-// host-side geometry for the band kernel; returns false when the shape does not fit shared memory
+// host-side geometry for the band kernel; returns false when the shape is better served by the generic kernel
 struct BandPlan {
   BandParams p;
-  int co;
   size_t smem_bytes;
   int64_t n_items;
   int grid;
 };
 
 inline bool plan_band(int dtype, int64_t planes, int in_h, int in_w, int out_h, int out_w, int pad_x0,
-                      int pad_y0, BandPlan* plan) {
+                      int pad_y0, const void* out, const void* noise, BandPlan* plan) {
+  if (out_w < 24 || out_h < 8) return false;  // tiny planes: launch-bound, one thread per output is as good
   const int es = dtype_size(dtype);
   const int slack = 32 / es;  // alignment shift (<16 B) + tail round-up (<16 B)
-  const int co = out_w > 64 ? 4 : (out_w > 32 ? 2 : 1);
-  // warp tasks per band: strips_x * R/kRS; aim for >= 8 tasks and <= ~40 KB per stage
-  const int strips_x = (out_w + 32 * co - 1) / (32 * co);
-  int r = kRS * ((kBandWarps + strips_x - 1) / strips_x);
-  const int64_t budget = 40 * 1024;
-  while (r > kRS && static_cast<int64_t>(r + 3) * in_w * es > budget) r -= kRS;
-  // grow small-plane bands up to the budget (fewer items, less halo)
-  while (r < out_h && static_cast<int64_t>(r + kRS + 3) * in_w * es <= budget / 2) r += kRS;
-  const int out_rounded = ((out_h + kRS - 1) / kRS) * kRS;
-  if (r > out_rounded) r = out_rounded;
-  if (r < kRS) r = kRS;
-  const int64_t stage_elems = (static_cast<int64_t>(r + 3) * in_w + slack + 15) / 16 * 16;
+  int lx_log2 = 5;
+  while (lx_log2 > 0 && (1 << (lx_log2 - 1)) * kCO >= out_w) --lx_log2;
+  const int lx = 1 << lx_log2, ly = 32 >> lx_log2;
+  const int strip_w = lx * kCO, strip_h = ly * kRS;
+  const int strips_x = out_w / strip_w > 0 ? out_w / strip_w : 1;  // full strips (the tail strip folds down the rows)
+  const int64_t budget = 36 * 1024;  // bytes per stage (3 stages x 2 CTAs per SM)
+  const int64_t plane_bytes = static_cast<int64_t>(in_h) * in_w * es;
+  BandParams& p = plan->p;
+  int r, bands, ppi = 1;
+  if (plane_bytes <= budget) {           // whole planes per item, several when small
+    r = out_h; bands = 1;
+    // enough planes to give every warp a task, within the budget
+    const int strips_y = (out_h + strip_h - 1) / strip_h;
+    const int tasks = strips_x * strips_y;
+    ppi = (kBandWarps + tasks - 1) / tasks;
+    const int64_t fit = budget / plane_bytes;
+    if (ppi > fit) ppi = static_cast<int>(fit);
+    if (ppi < 1) ppi = 1;
+    if (ppi > planes) ppi = static_cast<int>(planes);
+  } else {
+    // warp tasks per band: strips_x * R/strip_h; aim for >= 8 tasks within the budget
+    r = strip_h * ((kBandWarps + strips_x - 1) / strips_x);
+    while (r > strip_h && static_cast<int64_t>(r + 3) * in_w * es > budget) r -= strip_h;
+    if (static_cast<int64_t>(r + 3) * in_w * es > 64 * 1024) return false;  // rows too wide for the ring
+    if (r >= out_h) { r = out_h; }
+    bands = (out_h + r - 1) / r;
+    if (bands == 1) return false;  // cannot happen with plane_bytes > budget unless pads are huge
+  }
+  const int64_t rows_staged = (bands == 1) ? static_cast<int64_t>(ppi) * in_h : (r + 3);
+  const int64_t stage_elems = (rows_staged * in_w + slack + kFrontBytes / es + 16 / es + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(stage_elems) * es * kStages;
   if (smem > 200 * 1024) return false;
-  BandParams& p = plan->p;
   p.planes = planes; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
   p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
-  p.band_rows = r; p.bands = (out_h + r - 1) / r;
+  p.band_rows = r; p.bands = bands; p.planes_per_item = ppi;
   p.stage_elems = static_cast<int>(stage_elems);
+  p.lx_log2 = lx_log2;
+  const uintptr_t align = static_cast<uintptr_t>(4 * es);
+  p.vec_io = (out_w % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % align == 0) &&
+             (noise == nullptr || reinterpret_cast<uintptr_t>(noise) % align == 0);
   p.C = 1; p.act = 1; p.alpha = 0.f; p.scale = 1.f;
-  plan->co = co;
   plan->smem_bytes = smem;
-  plan->n_items = planes * p.bands;
+  plan->n_items = (bands == 1) ? (planes + ppi - 1) / ppi : planes * bands;
   const int ctas_per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
   const int64_t max_grid = static_cast<int64_t>(sm_count()) * ctas_per_sm;
   plan->grid = static_cast<int>(plan->n_items < max_grid ? plan->n_items : max_grid);
   return true;
 }
 
-template <typename T, int CO, bool FUSED>
+template <typename T, int IW4, bool FUSED>
 int launch_band_t(const BandPlan& pl, void* out, const void* in, const float* filt, int kh, int kw, const void* noise,
                   const float* nw, const float* bias, const float* row_scale, cudaStream_t st) {
-  auto kern = fir4_band_kernel<T, CO, FUSED>;
-  static thread_local size_t configured = 0;  // per instantiation, per thread: max smem opted in so far
-  if (pl.smem_bytes > configured) {
+  auto kern = fir4_band_kernel<T, IW4, FUSED>;
+  static thread_local bool configured = false;  // per instantiation, per thread
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(200 * 1024));
     if (e != cudaSuccess) return cuda_fail(e, "fir4_band smem opt-in");
-    configured = 200 * 1024;
+    configured = true;
   }
   kern<<<pl.grid, kBandThreads, pl.smem_bytes, st>>>(
       static_cast<T*>(out), static_cast<const T*>(in), filt, kh, kw, static_cast<const T*>(noise), nw, bias,
@@ -342,38 +676,47 @@ int launch_band_t(const BandPlan& pl, void* out, const void* in, const float* fi
   return GG_OK;
 }
 
-template <typename T, bool FUSED>
-int launch_band_co(const BandPlan& pl, void* out, const void* in, const float* filt, int kh, int kw, const void* noise,
-                   const float* nw, const float* bias, const float* row_scale, cudaStream_t st) {
-  switch (pl.co) {
-    case 4: return launch_band_t<T, 4, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
-    case 2: return launch_band_t<T, 2, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
-    default: return launch_band_t<T, 1, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
-  }
-}
-
 template <bool FUSED>
 int launch_band(int dtype, const BandPlan& pl, void* out, const void* in, const float* filt, int kh, int kw,
                 const void* noise, const float* nw, const float* bias, const float* row_scale,
                 cudaStream_t st) {
   switch (dtype) {
-    case GG_F32: return launch_band_co<float, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
-    case GG_F16: return launch_band_co<__half, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
-    case GG_BF16: return launch_band_co<__nv_bfloat16, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
+    case GG_F32:
+      switch (pl.p.in_w & 3) {  // row-to-row alignment rotation is a template parameter of the fp32 fast path
+        case 0: return launch_band_t<float, 0, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
+        case 1: return launch_band_t<float, 1, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
+        case 2: return launch_band_t<float, 2, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
+        default: return launch_band_t<float, 3, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
+      }
+    case GG_F16: return launch_band_t<__half, -1, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
+    case GG_BF16: return launch_band_t<__nv_bfloat16, -1, FUSED>(pl, out, in, filt, kh, kw, noise, nw, bias, row_scale, st);
     default: return fail(GG_ERR_UNSUPPORTED, "upfirdn2d: dtype %d not supported (f32/f16/bf16)", dtype);
   }
 }
 
 template <typename T>
-int launch_generic_t(void* out, const void* in, const float* filt, const GenericParams& gp, int64_t total,
-                     cudaStream_t st) {
+int launch_generic_t(void* out, const void* in, const float* filt, const GenericParams& gp, const Epilogue* ep,
+                     int64_t total, cudaStream_t st) {
   int64_t grid = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
   if (grid > cap) grid = cap;
-  upfirdn2d_generic_kernel<T><<<static_cast<unsigned>(grid), 256, 0, st>>>(
-      static_cast<T*>(out), static_cast<const T*>(in), filt, gp, total);
+  if (ep)
+    upfirdn2d_generic_kernel<T, true><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<T*>(out), static_cast<const T*>(in), filt, gp, *ep, total);
+  else
+    upfirdn2d_generic_kernel<T, false><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<T*>(out), static_cast<const T*>(in), filt, gp, Epilogue{}, total);
   GG_CHECK_LAUNCH("upfirdn2d_generic launch");
   return GG_OK;
+}
+
+inline int launch_generic(int dtype, void* out, const void* in, const float* filt, const GenericParams& gp,
+                          const Epilogue* ep, int64_t total, cudaStream_t st) {
+  switch (dtype) {
+    case GG_F32: return launch_generic_t<float>(out, in, filt, gp, ep, total, st);
+    case GG_F16: return launch_generic_t<__half>(out, in, filt, gp, ep, total, st);
+    default: return launch_generic_t<__nv_bfloat16>(out, in, filt, gp, ep, total, st);
+  }
 }
 
 inline int check_common(const char* who, const void* out, const void* in, const float* kernel, int dtype,
@@ -412,17 +755,13 @@ int gg_upfirdn2d(void* out, const void* in, const float* kernel, int dtype, int6
   if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kernel_h <= 4 && kernel_w <= 4 && in_h > 0 &&
       in_w > 0) {
     BandPlan pl;
-    if (plan_band(dtype, major, in_h, in_w, out_h, out_w, pad_x0, pad_y0, &pl))
+    if (plan_band(dtype, major, in_h, in_w, out_h, out_w, pad_x0, pad_y0, out, nullptr, &pl))
       return launch_band<false>(dtype, pl, out, in, kernel, kernel_h, kernel_w, nullptr, nullptr, nullptr,
                                 nullptr, st);
   }
   GenericParams gp{in_h, in_w, out_h, out_w, kernel_h, kernel_w, up_x, up_y, down_x, down_y, pad_x0, pad_y0};
   const int64_t total = major * out_h * static_cast<int64_t>(out_w);
-  switch (dtype) {
-    case GG_F32: return launch_generic_t<float>(out, in, kernel, gp, total, st);
-    case GG_F16: return launch_generic_t<__half>(out, in, kernel, gp, total, st);
-    default: return launch_generic_t<__nv_bfloat16>(out, in, kernel, gp, total, st);
-  }
+  return launch_generic(dtype, out, in, kernel, gp, nullptr, total, st);
 }
 
 int gg_blur_noise_bias_act(void* out, const void* in, const float* kernel, const void* noise,
@@ -442,8 +781,13 @@ int gg_blur_noise_bias_act(void* out, const void* in, const float* kernel, const
   if (major == 0) return GG_OK;
   if (in_h == 0 || in_w == 0) return fail(GG_ERR_BAD_ARG, "blur_noise_bias_act: empty input plane");
   BandPlan pl;
-  if (!plan_band(dtype, major, in_h, in_w, out_h, out_w, pad_x0, pad_y0, &pl))
-    return fail(GG_ERR_UNSUPPORTED, "blur_noise_bias_act: rows of %d elements do not fit the staging ring", in_w);
+  if (!plan_band(dtype, major, in_h, in_w, out_h, out_w, pad_x0, pad_y0, out, noise, &pl)) {
+    // tiny or very wide planes: generic gather kernel with the same fused epilogue
+    GenericParams gp{in_h, in_w, out_h, out_w, kernel_h, kernel_w, 1, 1, 1, 1, pad_x0, pad_y0};
+    Epilogue ep{noise, noise_weight, bias, row_scale, static_cast<int>(C), act, alpha, scale};
+    return launch_generic(dtype, out, in, kernel, gp, &ep, major * out_h * static_cast<int64_t>(out_w),
+                          static_cast<cudaStream_t>(stream));
+  }
   pl.p.C = static_cast<int>(C);
   pl.p.act = act;
   pl.p.alpha = alpha;

@@ -1,0 +1,586 @@
+// warp.cu -- antialiased (mip-mapped) bilinear grid sampling in one pass, forward and backward (sm_100a).
+//
+// Replaces reference models/spatial_transformers/antialiased_sampling.py:35-238 (MipmapWarp) which issues
+// ~30 ATen launches per call, materialises an (N, C, D, H, W) Gaussian *stack* (every level upsampled back
+// to full resolution), and synchronises with the host (`levels.max().ceil().item()`, :52) to size it.
+// Here the pyramid stays at its native resolutions (levels 1..E, built by mip_down_kernel) and ONE kernel
+// per direction evaluates, per output pixel: level of detail from the 4 grid neighbours (:62-97,197-210),
+// the two bracketing levels, the bilinear sample of each level *as if* it had been upsampled
+// (align_corners=False rules of F.interpolate nested inside those of F.grid_sample, :155-178) and the
+// linear blend (:227-237).  No stack, no host sync: levels above the batch maximum simply get weight 0.
+// Padding modes zeros/border/reflection follow ATen's grid_sampler (GridSampler.h) exactly, including the
+// corner in-bounds tests, so corner/level indices are identical integers.
+//
+// HBM-bound in principle (algorithmic bytes 4*N*(C*Hs*Ws + C*Ho*Wo + 2*Ho*Wo)) but at GANgealing's sizes
+// (3 x 128^2 .. 3 x 512^2 per sample) the whole working set is L2-resident and the win is launch count.
+#include "common.cuh"
+
+namespace gg {
+namespace {
+
+constexpr int kMaxLevels = 8;  // extra pyramid levels (1..E); MipmapWarp(max_num_levels=8) needs 7
+
+struct Pyramid {
+  int hs, ws;            // source size
+  int lp;                // reflect padding (left/top) applied before the pyramid when ws is not a power of two
+  int hp, wp;            // padded size
+  int extra;             // E
+  int64_t offset[kMaxLevels + 1];  // float offset of level i (1-based) inside the pyramid buffer
+  int64_t planes;
+};
+
+inline bool make_pyramid(int hs, int ws, int64_t planes, int extra, Pyramid* p, const char** why) {
+  p->hs = hs; p->ws = ws; p->planes = planes; p->extra = extra;
+  int lp = 0, rp = 0;
+  if (ws > 0 && (ws & (ws - 1)) != 0) {  // antialiased_sampling.py:130-137 (width decides, applied to both axes)
+    int target = 1;
+    while (target < ws) target <<= 1;
+    const int total = target - ws;
+    lp = total / 2;
+    rp = total - lp;
+  }
+  p->lp = lp;
+  p->hp = hs + lp + rp;
+  p->wp = ws + lp + rp;
+  if (lp >= hs || rp >= hs || lp >= ws || rp >= ws) { *why = "reflect padding to a power of two exceeds the source size"; return false; }
+  if (extra < 0 || extra > kMaxLevels) { *why = "too many mip levels"; return false; }
+  int64_t off = 0;
+  for (int i = 1; i <= extra; ++i) {
+    if ((p->hp >> (i - 1)) < 2 || (p->wp >> (i - 1)) < 2 || (p->hp % (1 << i)) != 0 || (p->wp % (1 << i)) != 0) {
+      *why = "source size is not divisible by 2^levels (the reference's Gaussian stack cannot be built either)";
+      return false;
+    }
+    p->offset[i] = off;
+    off += planes * (p->hp >> i) * static_cast<int64_t>(p->wp >> i);
+  }
+  p->offset[0] = off;  // total
+  return true;
+}
+
+__device__ __forceinline__ int reflect_idx(int j, int size) {  // ReflectionPad semantics (no edge repeat)
+  if (j < 0) j = -j;
+  if (j >= size) j = 2 * (size - 1) - j;
+  return j;
+}
+
+// level i (from level i-1): ReflectionPad2d(1) + [1,3,3,1]^2/64 stride 2  (antialiased_sampling.py:111-117)
+// SRC_LEVEL: the input is the source image seen through the virtual pow2 reflect padding.
+template <typename T, bool SRC_LEVEL>
+__global__ void mip_down_kernel(float* __restrict__ out, const T* __restrict__ in, int in_h, int in_w,
+                                int src_h, int src_w, int lp, int64_t total) {
+  const int oh = in_h >> 1, ow = in_w >> 1;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % ow);
+    const int64_t t = idx / ow;
+    const int y = static_cast<int>(t % oh);
+    const int64_t plane = t / oh;
+    const float f[4] = {1.f, 3.f, 3.f, 1.f};
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int yy = reflect_idx(2 * y + a - 1, in_h);
+      if (SRC_LEVEL) yy = reflect_idx(yy - lp, src_h);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        int xx = reflect_idx(2 * x + b - 1, in_w);
+        if (SRC_LEVEL) xx = reflect_idx(xx - lp, src_w);
+        const int64_t pos = SRC_LEVEL ? (plane * src_h + yy) * static_cast<int64_t>(src_w) + xx
+                                      : (plane * in_h + yy) * static_cast<int64_t>(in_w) + xx;
+        acc = fmaf(Cvt<T>::to_f(in[pos]), f[a] * f[b] * (1.f / 64.f), acc);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// adjoint of mip_down_kernel: grad_in += down^T(grad_out)   (atomics: reflected taps overlap)
+template <bool SRC_LEVEL>
+__global__ void mip_down_bwd_kernel(float* __restrict__ grad_in, const float* __restrict__ grad_out, int in_h,
+                                    int in_w, int src_h, int src_w, int lp, int64_t total) {
+  const int oh = in_h >> 1, ow = in_w >> 1;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % ow);
+    const int64_t t = idx / ow;
+    const int y = static_cast<int>(t % oh);
+    const int64_t plane = t / oh;
+    const float g = grad_out[idx];
+    if (g == 0.f) continue;
+    const float f[4] = {1.f, 3.f, 3.f, 1.f};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int yy = reflect_idx(2 * y + a - 1, in_h);
+      if (SRC_LEVEL) yy = reflect_idx(yy - lp, src_h);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        int xx = reflect_idx(2 * x + b - 1, in_w);
+        if (SRC_LEVEL) xx = reflect_idx(xx - lp, src_w);
+        const int64_t pos = SRC_LEVEL ? (plane * src_h + yy) * static_cast<int64_t>(src_w) + xx
+                                      : (plane * in_h + yy) * static_cast<int64_t>(in_w) + xx;
+        atomicAdd(grad_in + pos, g * (f[a] * f[b] * (1.f / 64.f)));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- coordinate transforms (ATen GridSampler.h)
+struct Coord {
+  float x;      // source coordinate after padding-mode handling
+  float mult;   // d x / d grid
+};
+
+__device__ __forceinline__ Coord reflect_coord(float in, int twice_low, int twice_high) {
+  Coord r;
+  if (twice_low == twice_high) { r.x = 0.f; r.mult = 0.f; return r; }
+  float mult = 1.f;
+  const float mn = static_cast<float>(twice_low) / 2.f;
+  const float span = static_cast<float>(twice_high - twice_low) / 2.f;
+  in = in - mn;
+  if (in < 0.f) { mult = -1.f; in = -in; }
+  const float extra = fmodf(in, span);
+  const int flips = static_cast<int>(floorf(in / span));
+  if (flips % 2 == 0) { r.x = extra + mn; r.mult = mult; }
+  else { r.x = span - extra + mn; r.mult = -mult; }
+  return r;
+}
+
+__device__ __forceinline__ Coord source_coord(float g, int size, int pad_mode) {
+  Coord c;
+  c.x = ((g + 1.f) * size - 1.f) / 2.f;   // align_corners = False
+  c.mult = static_cast<float>(size) / 2.f;
+  if (pad_mode == GG_PAD_BORDER) {
+    // clip_coordinates_set_grad: zero gradient AT and beyond the borders
+    if (c.x <= 0.f) { c.x = 0.f; c.mult = 0.f; }
+    else if (c.x >= static_cast<float>(size - 1)) { c.x = static_cast<float>(size - 1); c.mult = 0.f; }
+  } else if (pad_mode == GG_PAD_REFLECTION) {
+    const Coord r = reflect_coord(c.x, -1, 2 * size - 1);
+    c.x = r.x; c.mult *= r.mult;
+    if (c.x <= 0.f) { c.x = 0.f; c.mult = 0.f; }
+    else if (c.x >= static_cast<float>(size - 1)) { c.x = static_cast<float>(size - 1); c.mult = 0.f; }
+  }
+  return c;
+}
+
+// F.interpolate(bilinear, align_corners=False, scale_factor=2^i) source index of destination `dst`
+struct Up1D { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Up1D upsample_index(int dst, float inv_scale, int in_size) {
+  Up1D u;
+  float src = (static_cast<float>(dst) + 0.5f) * inv_scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  u.i0 = static_cast<int>(src);
+  u.i1 = u.i0 + ((u.i0 < in_size - 1) ? 1 : 0);
+  u.l1 = src - static_cast<float>(u.i0);
+  u.l0 = 1.f - u.l1;
+  return u;
+}
+
+struct LevelInfo {
+  float level;     // after both clamps
+  int l0, l1;      // floor / ceil
+  float w;         // level % 1
+  // gradient bookkeeping
+  float dmax;      // max clamped neighbour distance
+  int arg;         // 0 left, 1 right, 2 up, 3 down (first maximum)
+  float sq_arg;    // unclamped squared distance of the arg-max neighbour
+  float dx, dy;    // (other - c) of the arg-max neighbour, LOD coordinates
+  bool pass;       // level gradient flows (inside both clamps)
+};
+
+__device__ __forceinline__ LevelInfo level_of_detail(const float* __restrict__ grid_n, int oy, int ox, int ho, int wo,
+                                                     int hs, int ws, float max_level, float min_level) {
+  // antialiased_sampling.py:181-210 and :62-97
+  auto coord = [&](int y, int x, float& cx, float& cy) {
+    const float2 g = *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(y) * wo + x) * 2);
+    cx = (static_cast<float>(ws) - 1.f) * (g.x + 1.f) / 2.f;
+    cy = (static_cast<float>(hs) - 1.f) * (g.y + 1.f) / 2.f;
+  };
+  float cx, cy;
+  coord(oy, ox, cx, cy);
+  const int ny[4] = {oy, oy, max(oy - 1, 0), min(oy + 1, ho - 1)};
+  const int nx[4] = {max(ox - 1, 0), min(ox + 1, wo - 1), ox, ox};
+  LevelInfo li;
+  li.dmax = -1.f; li.arg = 0; li.sq_arg = 0.f; li.dx = 0.f; li.dy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float ox_, oy_;
+    coord(ny[k], nx[k], ox_, oy_);
+    const float dx = ox_ - cx, dy = oy_ - cy;
+    const float sq = dx * dx + dy * dy;
+    const float d = sqrtf(fmaxf(sq, 1.f));
+    if (d > li.dmax) { li.dmax = d; li.arg = k; li.sq_arg = sq; li.dx = dx; li.dy = dy; }
+  }
+  const float raw = log2f(li.dmax);
+  float lvl = fminf(fmaxf(raw, 0.f), max_level);
+  li.pass = (raw >= 0.f) && (raw <= max_level) && (lvl >= min_level);
+  lvl = fmaxf(lvl, min_level);
+  li.level = lvl;
+  const float fl = floorf(lvl);
+  li.l0 = static_cast<int>(fl);
+  li.l1 = static_cast<int>(ceilf(lvl));
+  li.w = lvl - fl;
+  return li;
+}
+
+struct SampleGeom {   // bilinear corners of one output pixel (shared by all levels and channels)
+  int x0, y0;
+  float wx0, wx1, wy0, wy1;   // wx1 = ix - x0, wx0 = x1 - ix ...
+  bool in_x0, in_x1, in_y0, in_y1;
+  float mx, my;               // d ix / d gx, d iy / d gy
+};
+
+__device__ __forceinline__ SampleGeom sample_geom(float gx, float gy, int hs, int ws, int pad_mode) {
+  SampleGeom s;
+  const Coord cx = source_coord(gx, ws, pad_mode);
+  const Coord cy = source_coord(gy, hs, pad_mode);
+  const float fx = floorf(cx.x), fy = floorf(cy.x);
+  s.x0 = static_cast<int>(fx); s.y0 = static_cast<int>(fy);
+  s.wx1 = cx.x - fx; s.wx0 = (fx + 1.f) - cx.x;
+  s.wy1 = cy.x - fy; s.wy0 = (fy + 1.f) - cy.x;
+  s.in_x0 = s.x0 >= 0 && s.x0 < ws; s.in_x1 = s.x0 + 1 >= 0 && s.x0 + 1 < ws;
+  s.in_y0 = s.y0 >= 0 && s.y0 < hs; s.in_y1 = s.y0 + 1 >= 0 && s.y0 + 1 < hs;
+  s.mx = cx.mult; s.my = cy.mult;
+  return s;
+}
+
+// value of pyramid level `lev` (>= 1), upsampled to full resolution, at source pixel (y, x)
+__device__ __forceinline__ float level_value(const float* __restrict__ lvl_plane, int lh, int lw, float inv_scale,
+                                             int y, int x, int lp) {
+  const Up1D uy = upsample_index(y + lp, inv_scale, lh);
+  const Up1D ux = upsample_index(x + lp, inv_scale, lw);
+  const float v00 = lvl_plane[static_cast<int64_t>(uy.i0) * lw + ux.i0];
+  const float v01 = lvl_plane[static_cast<int64_t>(uy.i0) * lw + ux.i1];
+  const float v10 = lvl_plane[static_cast<int64_t>(uy.i1) * lw + ux.i0];
+  const float v11 = lvl_plane[static_cast<int64_t>(uy.i1) * lw + ux.i1];
+  return uy.l0 * (ux.l0 * v00 + ux.l1 * v01) + uy.l1 * (ux.l0 * v10 + ux.l1 * v11);
+}
+
+struct WarpParams {
+  int64_t n; int c; int hs, ws, ho, wo;
+  int pad_mode;
+  float max_level, min_level;
+  int lp, hp, wp, extra;
+  int64_t offset[kMaxLevels + 1];
+};
+
+// bilinear sample of level `lev` for channel plane; returns value and (optionally) d/dix, d/diy
+template <typename T, bool GRAD>
+__device__ __forceinline__ float sample_level(const T* __restrict__ src_plane, const float* __restrict__ pyr,
+                                              const WarpParams& p, int64_t plane, int lev, const SampleGeom& s,
+                                              float* dix, float* diy) {
+  float v[2][2];
+  const float* lvl_plane = nullptr;
+  int lh = 0, lw = 0;
+  float inv = 1.f;
+  if (lev > 0) {
+    lh = p.hp >> lev; lw = p.wp >> lev;
+    lvl_plane = pyr + p.offset[lev] + plane * lh * static_cast<int64_t>(lw);
+    inv = 1.f / static_cast<float>(1 << lev);
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const bool ok = (a ? s.in_y1 : s.in_y0) && (b ? s.in_x1 : s.in_x0);
+      float val = 0.f;
+      if (ok) {
+        const int y = s.y0 + a, x = s.x0 + b;
+        val = (lev == 0) ? Cvt<T>::to_f(src_plane[static_cast<int64_t>(y) * p.ws + x])
+                         : level_value(lvl_plane, lh, lw, inv, y, x, p.lp);
+      }
+      v[a][b] = val;
+    }
+  if (GRAD) {
+    // ATen grid_sampler_2d_backward: gix -= nw*(iy_se - iy) ... with our weights
+    *dix = -v[0][0] * s.wy0 + v[0][1] * s.wy0 - v[1][0] * s.wy1 + v[1][1] * s.wy1;
+    *diy = -v[0][0] * s.wx0 - v[0][1] * s.wx1 + v[1][0] * s.wx0 + v[1][1] * s.wx1;
+  }
+  return v[0][0] * (s.wx0 * s.wy0) + v[0][1] * (s.wx1 * s.wy0) + v[1][0] * (s.wx0 * s.wy1) + v[1][1] * (s.wx1 * s.wy1);
+}
+
+template <typename T, bool MIP>
+__global__ void __launch_bounds__(256)
+warp_fwd_kernel(T* __restrict__ out, float* __restrict__ levels_out, const T* __restrict__ src,
+                const float* __restrict__ pyr, const float* __restrict__ grid, const __grid_constant__ WarpParams p,
+                int64_t total) {
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % p.wo);
+    const int64_t t = idx / p.wo;
+    const int oy = static_cast<int>(t % p.ho);
+    const int64_t n = t / p.ho;
+    const float* grid_n = grid + n * p.ho * static_cast<int64_t>(p.wo) * 2;
+    const float2 g = *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(oy) * p.wo + ox) * 2);
+    const SampleGeom s = sample_geom(g.x, g.y, p.hs, p.ws, p.pad_mode);
+    int l0 = 0, l1 = 0;
+    float w = 0.f;
+    if (MIP) {
+      const LevelInfo li = level_of_detail(grid_n, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
+      l0 = li.l0; l1 = li.l1; w = li.w;
+      if (levels_out) levels_out[idx] = li.level;
+    }
+    for (int c = 0; c < p.c; ++c) {
+      const int64_t plane = n * p.c + c;
+      const T* src_plane = src + plane * p.hs * static_cast<int64_t>(p.ws);
+      const float o0 = sample_level<T, false>(src_plane, pyr, p, plane, l0, s, nullptr, nullptr);
+      float o = o0;
+      if (MIP && l1 != l0) {
+        const float o1 = sample_level<T, false>(src_plane, pyr, p, plane, l1, s, nullptr, nullptr);
+        o = o0 + w * (o1 - o0);
+      }
+      out[(plane * p.ho + oy) * static_cast<int64_t>(p.wo) + ox] = Cvt<T>::from_f(o);
+    }
+  }
+}
+
+// scatter `g` (gradient w.r.t. the bilinear sample of level `lev`) into grad_src / grad_pyr
+__device__ __forceinline__ void scatter_level(float* __restrict__ grad_src, float* __restrict__ grad_pyr,
+                                              const WarpParams& p, int64_t plane, int lev, const SampleGeom& s, float g) {
+  if (g == 0.f) return;
+  int lh = 0, lw = 0;
+  float inv = 1.f;
+  float* lvl_plane = nullptr;
+  if (lev > 0) {
+    lh = p.hp >> lev; lw = p.wp >> lev;
+    lvl_plane = grad_pyr + p.offset[lev] + plane * lh * static_cast<int64_t>(lw);
+    inv = 1.f / static_cast<float>(1 << lev);
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const bool ok = (a ? s.in_y1 : s.in_y0) && (b ? s.in_x1 : s.in_x0);
+      if (!ok) continue;
+      const float wt = (a ? s.wy1 : s.wy0) * (b ? s.wx1 : s.wx0) * g;
+      const int y = s.y0 + a, x = s.x0 + b;
+      if (lev == 0) {
+        atomicAdd(grad_src + (plane * p.hs + y) * static_cast<int64_t>(p.ws) + x, wt);
+      } else {
+        const Up1D uy = upsample_index(y + p.lp, inv, lh);
+        const Up1D ux = upsample_index(x + p.lp, inv, lw);
+        atomicAdd(lvl_plane + static_cast<int64_t>(uy.i0) * lw + ux.i0, wt * uy.l0 * ux.l0);
+        atomicAdd(lvl_plane + static_cast<int64_t>(uy.i0) * lw + ux.i1, wt * uy.l0 * ux.l1);
+        atomicAdd(lvl_plane + static_cast<int64_t>(uy.i1) * lw + ux.i0, wt * uy.l1 * ux.l0);
+        atomicAdd(lvl_plane + static_cast<int64_t>(uy.i1) * lw + ux.i1, wt * uy.l1 * ux.l1);
+      }
+    }
+}
+
+template <typename T, bool MIP>
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(float* __restrict__ grad_src, float* __restrict__ grad_pyr, float* __restrict__ grad_grid,
+                const T* __restrict__ grad_out, const T* __restrict__ src, const float* __restrict__ pyr,
+                const float* __restrict__ grid, const __grid_constant__ WarpParams p, int64_t total) {
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % p.wo);
+    const int64_t t = idx / p.wo;
+    const int oy = static_cast<int>(t % p.ho);
+    const int64_t n = t / p.ho;
+    const int64_t grid_off = n * p.ho * static_cast<int64_t>(p.wo) * 2;
+    const float* grid_n = grid + grid_off;
+    const float2 g = *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(oy) * p.wo + ox) * 2);
+    const SampleGeom s = sample_geom(g.x, g.y, p.hs, p.ws, p.pad_mode);
+    LevelInfo li;
+    li.l0 = li.l1 = 0; li.w = 0.f; li.pass = false;
+    if (MIP) li = level_of_detail(grid_n, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
+    float gix = 0.f, giy = 0.f, glevel = 0.f;
+    for (int c = 0; c < p.c; ++c) {
+      const int64_t plane = n * p.c + c;
+      const float go = Cvt<T>::to_f(grad_out[(plane * p.ho + oy) * static_cast<int64_t>(p.wo) + ox]);
+      const T* src_plane = src + plane * p.hs * static_cast<int64_t>(p.ws);
+      float dx0 = 0.f, dy0 = 0.f, dx1 = 0.f, dy1 = 0.f;
+      const bool two = MIP && (li.l1 != li.l0);
+      if (grad_grid) {
+        const float o0 = sample_level<T, true>(src_plane, pyr, p, plane, li.l0, s, &dx0, &dy0);
+        float k0 = 1.f;
+        if (two) {
+          const float o1 = sample_level<T, true>(src_plane, pyr, p, plane, li.l1, s, &dx1, &dy1);
+          k0 = 1.f - li.w;
+          glevel += go * (o1 - o0);
+        }
+        gix += go * (k0 * dx0 + (two ? li.w * dx1 : 0.f));
+        giy += go * (k0 * dy0 + (two ? li.w * dy1 : 0.f));
+      }
+      if (grad_src) {
+        scatter_level(grad_src, grad_pyr, p, plane, li.l0, s, go * (two ? 1.f - li.w : 1.f));
+        if (two) scatter_level(grad_src, grad_pyr, p, plane, li.l1, s, go * li.w);
+      }
+    }
+    if (grad_grid) {
+      float* gg_n = grad_grid + grid_off;
+      float ax = gix * s.mx, ay = giy * s.my;
+      if (MIP && li.pass && glevel != 0.f && li.sq_arg >= 1.f) {
+        // level = log2(dmax); dmax = sqrt(sq) of the arg-max neighbour (clamp(min=1) passes: sq >= 1)
+        const float g_sq = glevel / (li.dmax * 0.6931471805599453f) * (0.5f / li.dmax);
+        const float sx = (static_cast<float>(p.ws) - 1.f) * 0.5f, sy = (static_cast<float>(p.hs) - 1.f) * 0.5f;
+        const float gox = 2.f * li.dx * g_sq * sx, goy = 2.f * li.dy * g_sq * sy;
+        const int ny = (li.arg == 2) ? max(oy - 1, 0) : (li.arg == 3 ? min(oy + 1, p.ho - 1) : oy);
+        const int nx = (li.arg == 0) ? max(ox - 1, 0) : (li.arg == 1 ? min(ox + 1, p.wo - 1) : ox);
+        atomicAdd(gg_n + (static_cast<int64_t>(ny) * p.wo + nx) * 2 + 0, gox);
+        atomicAdd(gg_n + (static_cast<int64_t>(ny) * p.wo + nx) * 2 + 1, goy);
+        ax -= gox; ay -= goy;
+      }
+      atomicAdd(gg_n + (static_cast<int64_t>(oy) * p.wo + ox) * 2 + 0, ax);
+      atomicAdd(gg_n + (static_cast<int64_t>(oy) * p.wo + ox) * 2 + 1, ay);
+    }
+  }
+}
+
+inline int grid_for(int64_t total, int threads) {
+  int64_t g = (total + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+inline int fill_params(WarpParams* wp, int64_t n, int c, int hs, int ws, int ho, int wo, int pad_mode, int extra,
+                       float max_level, float min_level) {
+  if (n < 0 || c < 0 || hs < 1 || ws < 1 || ho < 0 || wo < 0) return fail(GG_ERR_BAD_ARG, "mipmap_warp: bad shape");
+  if (pad_mode < 0 || pad_mode > 2) return fail(GG_ERR_BAD_ARG, "mipmap_warp: padding mode must be 0/1/2");
+  Pyramid py;
+  const char* why = "";
+  if (!make_pyramid(hs, ws, n * c, extra, &py, &why)) return fail(GG_ERR_UNSUPPORTED, "mipmap_warp: %s", why);
+  if (extra > 0 && (ceilf(max_level) > extra || ceilf(min_level) > extra))
+    return fail(GG_ERR_BAD_ARG, "mipmap_warp: pyramid has %d extra levels but levels up to %g are requested", extra,
+                fmaxf(max_level, min_level));
+  wp->n = n; wp->c = c; wp->hs = hs; wp->ws = ws; wp->ho = ho; wp->wo = wo; wp->pad_mode = pad_mode;
+  wp->max_level = max_level; wp->min_level = min_level;
+  wp->lp = py.lp; wp->hp = py.hp; wp->wp = py.wp; wp->extra = extra;
+  for (int i = 0; i <= kMaxLevels; ++i) wp->offset[i] = (i <= extra) ? py.offset[i] : 0;
+  return GG_OK;
+}
+
+template <typename T>
+int build_t(float* pyr, const void* src, const Pyramid& py, cudaStream_t st) {
+  for (int i = 1; i <= py.extra; ++i) {
+    const int in_h = py.hp >> (i - 1), in_w = py.wp >> (i - 1);
+    const int64_t total = py.planes * (in_h >> 1) * static_cast<int64_t>(in_w >> 1);
+    if (total == 0) continue;
+    float* out = pyr + py.offset[i];
+    if (i == 1)
+      mip_down_kernel<T, true><<<grid_for(total, 256), 256, 0, st>>>(out, static_cast<const T*>(src), in_h, in_w,
+                                                                    py.hs, py.ws, py.lp, total);
+    else
+      mip_down_kernel<float, false><<<grid_for(total, 256), 256, 0, st>>>(out, pyr + py.offset[i - 1], in_h, in_w,
+                                                                         py.hs, py.ws, py.lp, total);
+    GG_CHECK_LAUNCH("mip_down launch");
+  }
+  return GG_OK;
+}
+
+}  // namespace
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int64_t gg_mipmap_pyramid_elems(int64_t planes, int hs, int ws, int extra_levels) {
+  Pyramid py;
+  const char* why = "";
+  if (planes < 0 || hs < 1 || ws < 1 || !make_pyramid(hs, ws, planes, extra_levels, &py, &why)) return -1;
+  return py.offset[0];
+}
+
+int gg_mipmap_build(float* pyramid, const void* src, int dtype, int64_t planes, int hs, int ws, int extra_levels,
+                    void* stream) {
+  Pyramid py;
+  const char* why = "";
+  if (planes < 0 || hs < 1 || ws < 1) return fail(GG_ERR_BAD_ARG, "mipmap_build: bad shape");
+  if (!make_pyramid(hs, ws, planes, extra_levels, &py, &why)) return fail(GG_ERR_UNSUPPORTED, "mipmap_build: %s", why);
+  if (planes == 0 || extra_levels == 0) return GG_OK;
+  if (!pyramid || !src) return fail(GG_ERR_BAD_ARG, "mipmap_build: null tensor");
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case GG_F32: return build_t<float>(pyramid, src, py, st);
+    case GG_F16: return build_t<__half>(pyramid, src, py, st);
+    case GG_BF16: return build_t<__nv_bfloat16>(pyramid, src, py, st);
+    default: return fail(GG_ERR_UNSUPPORTED, "mipmap_build: dtype %d not supported", dtype);
+  }
+}
+
+int gg_mipmap_build_backward(float* grad_src, float* grad_pyramid, int64_t planes, int hs, int ws, int extra_levels,
+                             void* stream) {
+  Pyramid py;
+  const char* why = "";
+  if (planes < 0 || hs < 1 || ws < 1) return fail(GG_ERR_BAD_ARG, "mipmap_build_backward: bad shape");
+  if (!make_pyramid(hs, ws, planes, extra_levels, &py, &why)) return fail(GG_ERR_UNSUPPORTED, "mipmap_build_backward: %s", why);
+  if (planes == 0 || extra_levels == 0) return GG_OK;
+  if (!grad_src || !grad_pyramid) return fail(GG_ERR_BAD_ARG, "mipmap_build_backward: null tensor");
+  auto st = static_cast<cudaStream_t>(stream);
+  for (int i = py.extra; i >= 1; --i) {  // coarse to fine: grad_{i-1} += down^T(grad_i)
+    const int in_h = py.hp >> (i - 1), in_w = py.wp >> (i - 1);
+    const int64_t total = py.planes * (in_h >> 1) * static_cast<int64_t>(in_w >> 1);
+    const float* go = grad_pyramid + py.offset[i];
+    if (i == 1)
+      mip_down_bwd_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(grad_src, go, in_h, in_w, py.hs, py.ws, py.lp, total);
+    else
+      mip_down_bwd_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(grad_pyramid + py.offset[i - 1], go, in_h, in_w,
+                                                                       py.hs, py.ws, py.lp, total);
+    GG_CHECK_LAUNCH("mip_down_bwd launch");
+  }
+  return GG_OK;
+}
+
+int gg_mipmap_warp_forward(void* out, float* levels_out, const void* src, const float* pyramid, const float* grid,
+                           int dtype, int64_t N, int C, int hs, int ws, int ho, int wo, int extra_levels,
+                           float max_level, float min_level, int padding_mode, void* stream) {
+  WarpParams wp;
+  int rc = fill_params(&wp, N, C, hs, ws, ho, wo, padding_mode, extra_levels, max_level, min_level);
+  if (rc != GG_OK) return rc;
+  const int64_t total = N * ho * static_cast<int64_t>(wo);
+  if (total == 0 || C == 0) return GG_OK;
+  if (!out || !src || !grid || (extra_levels > 0 && !pyramid)) return fail(GG_ERR_BAD_ARG, "mipmap_warp_forward: null tensor");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int gridsz = grid_for(total, 256);
+#define GG_FWD(T_)                                                                                               \
+  if (extra_levels > 0)                                                                                          \
+    warp_fwd_kernel<T_, true><<<gridsz, 256, 0, st>>>(static_cast<T_*>(out), levels_out, static_cast<const T_*>(src), \
+                                                      pyramid, grid, wp, total);                               \
+  else                                                                                                           \
+    warp_fwd_kernel<T_, false><<<gridsz, 256, 0, st>>>(static_cast<T_*>(out), levels_out, static_cast<const T_*>(src), \
+                                                       pyramid, grid, wp, total)
+  switch (dtype) {
+    case GG_F32: GG_FWD(float); break;
+    case GG_F16: GG_FWD(__half); break;
+    case GG_BF16: GG_FWD(__nv_bfloat16); break;
+    default: return fail(GG_ERR_UNSUPPORTED, "mipmap_warp_forward: dtype %d not supported", dtype);
+  }
+#undef GG_FWD
+  GG_CHECK_LAUNCH("warp_fwd launch");
+  return GG_OK;
+}
+
+int gg_mipmap_warp_backward(float* grad_src, float* grad_pyramid, float* grad_grid, const void* grad_out,
+                            const void* src, const float* pyramid, const float* grid, int dtype, int64_t N, int C,
+                            int hs, int ws, int ho, int wo, int extra_levels, float max_level, float min_level,
+                            int padding_mode, void* stream) {
+  WarpParams wp;
+  int rc = fill_params(&wp, N, C, hs, ws, ho, wo, padding_mode, extra_levels, max_level, min_level);
+  if (rc != GG_OK) return rc;
+  const int64_t total = N * ho * static_cast<int64_t>(wo);
+  if (total == 0 || C == 0) return GG_OK;
+  if (!grad_out || !src || !grid || (extra_levels > 0 && !pyramid)) return fail(GG_ERR_BAD_ARG, "mipmap_warp_backward: null tensor");
+  if (grad_src && extra_levels > 0 && !grad_pyramid) return fail(GG_ERR_BAD_ARG, "mipmap_warp_backward: grad_src needs grad_pyramid");
+  if (!grad_src && !grad_grid) return GG_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  const int gridsz = grid_for(total, 256);
+#define GG_BWD(T_)                                                                                               \
+  if (extra_levels > 0)                                                                                          \
+    warp_bwd_kernel<T_, true><<<gridsz, 256, 0, st>>>(grad_src, grad_pyramid, grad_grid,                        \
+        static_cast<const T_*>(grad_out), static_cast<const T_*>(src), pyramid, grid, wp, total);               \
+  else                                                                                                           \
+    warp_bwd_kernel<T_, false><<<gridsz, 256, 0, st>>>(grad_src, grad_pyramid, grad_grid,                       \
+        static_cast<const T_*>(grad_out), static_cast<const T_*>(src), pyramid, grid, wp, total)
+  switch (dtype) {
+    case GG_F32: GG_BWD(float); break;
+    case GG_F16: GG_BWD(__half); break;
+    case GG_BF16: GG_BWD(__nv_bfloat16); break;
+    default: return fail(GG_ERR_UNSUPPORTED, "mipmap_warp_backward: dtype %d not supported", dtype);
+  }
+#undef GG_BWD
+  GG_CHECK_LAUNCH("warp_bwd launch");
+  return GG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+"""Warp / MipmapWarp / BilinearDownsample -- drop-ins for reference
+models/spatial_transformers/antialiased_sampling.py on sm_100a.
+
+`MipmapWarp(max_num_levels).forward(inputs, grid, min_level=0.0, padding_mode='border')` and
+`Warp().forward(inputs, grid, padding_mode='border')` keep the reference call signatures, the
+`blur_filter` buffer and the `levels_map` attribute.  One fused kernel per direction
+(gg_mipmap_warp_forward / _backward) replaces the ~30 launches and the `.item()` host sync of the
+reference's forward (antialiased_sampling.py:35-60); see csrc/warp.cu for the algorithm.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _lib
+
+
+def feasible_levels(h, w, wanted):
+    """How many pyramid levels (beyond level 0) a source of this size can host (<= wanted)."""
+    lib = _lib.load()
+    e = wanted
+    while e > 0 and lib.gg_mipmap_pyramid_elems(1, h, w, e) < 0:
+        e -= 1
+    return e
+
+
+class _MipmapWarp(Function):
+    @staticmethod
+    def forward(ctx, inputs, grid, max_level, min_level, pad_mode, extra):
+        _lib.require_cuda(inputs, grid)
+        if inputs.dim() != 4 or grid.dim() != 4 or grid.shape[-1] != 2 or grid.shape[0] != inputs.shape[0]:
+            raise RuntimeError("warp: expected inputs (N, C, H, W) and grid (N, Ho, Wo, 2), got %s and %s" %
+                               (tuple(inputs.shape), tuple(grid.shape)))
+        lib = _lib.load()
+        x = inputs.contiguous()
+        g = grid.float().contiguous()
+        n, c, hs, ws = x.shape
+        ho, wo = g.shape[1], g.shape[2]
+        code = _lib.dtype_code(x)
+        st = _lib.stream()
+        pyr = None
+        if extra > 0:
+            elems = lib.gg_mipmap_pyramid_elems(n * c, hs, ws, extra)
+            if elems < 0:
+                raise RuntimeError("MipmapWarp: a %dx%d source cannot host %d mip levels" % (hs, ws, extra))
+            pyr = torch.empty(max(int(elems), 1), dtype=torch.float32, device=x.device)
+            _lib.check(lib.gg_mipmap_build(pyr.data_ptr(), x.data_ptr(), code, n * c, hs, ws, extra, st), "gg_mipmap_build")
+        out = torch.empty((n, c, ho, wo), dtype=x.dtype, device=x.device)
+        levels = torch.empty((n, ho, wo), dtype=torch.float32, device=x.device) if extra > 0 else None
+        rc = lib.gg_mipmap_warp_forward(out.data_ptr(), _lib.ptr(levels), x.data_ptr(), _lib.ptr(pyr), g.data_ptr(), code,
+                                        n, c, hs, ws, ho, wo, extra, max_level, min_level, pad_mode, st)
+        _lib.check(rc, "gg_mipmap_warp_forward")
+        ctx.save_for_backward(x, g, pyr)
+        ctx.cfg = (max_level, min_level, pad_mode, extra, grid.dtype)
+        if levels is None:
+            levels = out.new_zeros(())
+        ctx.mark_non_differentiable(levels)
+        return out, levels
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out, _grad_levels):
+        x, g, pyr = ctx.saved_tensors
+        max_level, min_level, pad_mode, extra, grid_dtype = ctx.cfg
+        need_x, need_g = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        lib = _lib.load()
+        n, c, hs, ws = x.shape
+        ho, wo = g.shape[1], g.shape[2]
+        st = _lib.stream()
+        go = grad_out.contiguous()
+        if go.dtype != x.dtype:
+            go = go.to(x.dtype)
+        grad_src = torch.zeros(x.shape, dtype=torch.float32, device=x.device) if need_x else None
+        grad_pyr = torch.zeros_like(pyr) if (need_x and pyr is not None) else None
+        grad_grid = torch.zeros(g.shape, dtype=torch.float32, device=x.device) if need_g else None
+        rc = lib.gg_mipmap_warp_backward(_lib.ptr(grad_src), _lib.ptr(grad_pyr), _lib.ptr(grad_grid), go.data_ptr(),
+                                         x.data_ptr(), _lib.ptr(pyr), g.data_ptr(), _lib.dtype_code(x), n, c, hs, ws,
+                                         ho, wo, extra, max_level, min_level, pad_mode, st)
+        _lib.check(rc, "gg_mipmap_warp_backward")
+        if need_x and extra > 0:
+            rc = lib.gg_mipmap_build_backward(grad_src.data_ptr(), grad_pyr.data_ptr(), n * c, hs, ws, extra, st)
+            _lib.check(rc, "gg_mipmap_build_backward")
+        if grad_src is not None and grad_src.dtype != x.dtype:
+            grad_src = grad_src.to(x.dtype)
+        if grad_grid is not None and grad_grid.dtype != grid_dtype:
+            grad_grid = grad_grid.to(grid_dtype)
+        return grad_src, grad_grid, None, None, None, None
+
+
+def _pad_code(padding_mode):
+    try:
+        return _lib.PAD_MODES[padding_mode]
+    except KeyError:
+        raise RuntimeError("padding_mode must be 'zeros', 'border' or 'reflection', got %r" % (padding_mode,))
+
+
+def grid_sample_bilinear(inputs, grid, padding_mode="border"):
+    """F.grid_sample(inputs, grid, padding_mode=..., align_corners=False) through the fused kernel (no mip levels)."""
+    return _MipmapWarp.apply(inputs, grid, 0.0, 0.0, _pad_code(padding_mode), 0)[0]
+
+
+class Warp(nn.Module):
+    """Spatial transform without anti-aliasing (reference antialiased_sampling.py:9-16)."""
+
+    def forward(self, inputs, grid, padding_mode="border"):
+        return grid_sample_bilinear(inputs, grid, padding_mode)
+
+
+class MipmapWarp(nn.Module):
+    """Spatial transform with mipmap anti-aliasing (reference antialiased_sampling.py:19-60)."""
+
+    def __init__(self, max_num_levels=8):
+        super().__init__()
+        self.max_num_levels = max_num_levels
+        f = torch.tensor([1.0, 3.0, 3.0, 1.0])
+        f = f[:, None] * f[None, :]
+        self.register_buffer("blur_filter", (f / f.sum())[None, None])  # state-dict parity; the kernel hard-codes it
+        self._levels = None
+
+    @property
+    def levels_map(self):
+        """levels / (max_num_levels - 1), as the reference stores after every forward (:59)."""
+        if self._levels is None:
+            return None
+        return self._levels / (self.max_num_levels - 1.0)
+
+    def forward(self, inputs, grid, min_level=0.0, padding_mode="border"):
+        max_level = float(self.max_num_levels) - 1.0
+        wanted = int(math.ceil(max(max_level, float(min_level), 0.0)))
+        extra = feasible_levels(inputs.shape[2], inputs.shape[3], wanted)
+        if extra < wanted:  # tiny source: the reference only fails if such a level is actually selected
+            max_level = min(max_level, float(extra))
+            min_level = min(float(min_level), float(extra))
+        out, levels = _MipmapWarp.apply(inputs, grid, max_level, float(min_level), _pad_code(padding_mode), extra)
+        self._levels = levels if extra > 0 else torch.zeros(grid.shape[:3], device=grid.device)
+        return out
+
+    @staticmethod
+    def get_max_coord_distance(coords):
+        """Max distance to the four replicate-padded neighbours, each clamped at 1 (reference :62-97);
+        provided for API parity (plain tensor ops, not on the hot path)."""
+        p = F.pad(coords.permute(0, 3, 1, 2), (1, 1, 1, 1), mode="replicate").permute(0, 2, 3, 1)
+        around = (p[:, 1:-1, :-2], p[:, 1:-1, 2:], p[:, :-2, 1:-1], p[:, 2:, 1:-1])
+        return torch.stack([((o - coords) ** 2).sum(3).clamp(min=1.0).sqrt() for o in around]).max(dim=0).values
+
+
+class BilinearDownsample(nn.Module):
+    """Reflect-pad + separable tent filter with stride (reference antialiased_sampling.py:241-256).
+    Same buffers (`kernel_horz`, `kernel_vert`); SURVEY.md 8(f) rank 1 -- still two cuDNN depthwise convs here."""
+
+    def __init__(self, stride, channels):
+        super().__init__()
+        self.stride = stride
+        self.channels = channels
+        ramp = np.arange(1, 2 * stride + 1, 2)
+        tent = np.concatenate((ramp, ramp[::-1]))
+        tent = torch.Tensor(tent / np.sum(tent))
+        self.register_buffer("kernel_horz", tent[None, None, None, :].repeat((channels, 1, 1, 1)))
+        self.register_buffer("kernel_vert", tent[None, None, :, None].repeat((channels, 1, 1, 1)))
+        self.refl = nn.ReflectionPad2d(int(stride / 2))
+
+    def forward(self, input):
+        rows = F.conv2d(self.refl(input), self.kernel_horz, stride=(1, self.stride), groups=self.channels)
+        return F.conv2d(rows, self.kernel_vert, stride=(self.stride, 1), groups=self.channels)

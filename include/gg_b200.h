@@ -121,6 +121,78 @@ GG_API int gg_blur_noise_bias_act(void* out, const void* in, const float* kernel
                                   int pad_y0, int pad_y1, int act, float alpha, float scale,
                                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Antialiased (mip-mapped) bilinear grid sampling -- replaces MipmapWarp / Warp
+ *   reference: models/spatial_transformers/antialiased_sampling.py:9-16 (Warp), :35-238 (MipmapWarp)
+ *   and the ATen kernels behind F.grid_sample(align_corners=False) / F.interpolate / F.conv2d they call.
+ *
+ *   Pyramid: level i (1..extra_levels) = i applications of [ReflectionPad2d(1) -> depthwise
+ *   [1,3,3,1]^2/64 stride-2 conv] (:111-117) to the source, after the reference's reflect padding to the
+ *   next power of two when the width is not one (:130-137).  Stored fp32, level-major, at native
+ *   resolution: gg_mipmap_pyramid_elems() floats (returns -1 if the size cannot host that many levels,
+ *   exactly when the reference's stack construction would fail).
+ *
+ *   forward : out[n,c,y,x] = lerp(S_floor(l), S_ceil(l), l mod 1),  S_i = bilinear sample of level i
+ *             upsampled x2^i (align_corners=False) at grid[n,y,x]; l = clamp(log2(max 4-neighbour
+ *             distance of the (size-1)-scaled coordinates, each >= 1), 0, max_level) clamped >= min_level
+ *             (:62-97, :181-210).  extra_levels == 0: plain bilinear grid_sample (Warp).
+ *             levels_out (N,Ho,Wo) fp32 receives l (NULL to skip).
+ *   backward: gradients w.r.t. the source (through every pyramid level; grad_src/grad_pyramid are fp32,
+ *             ZERO-INITIALISED by the caller and accumulated with atomics; finish with
+ *             gg_mipmap_build_backward) and w.r.t. the grid (sampling position AND level-of-detail terms,
+ *             like autograd through the reference; grad_grid fp32, zero-initialised by the caller).
+ *   src/out/grad_out: `dtype`; grid: fp32 (N, Ho, Wo, 2), normalised to [-1, 1].
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int64_t gg_mipmap_pyramid_elems(int64_t planes, int hs, int ws, int extra_levels);
+GG_API int gg_mipmap_build(float* pyramid, const void* src, int dtype, int64_t planes, int hs, int ws,
+                           int extra_levels, void* stream);
+GG_API int gg_mipmap_build_backward(float* grad_src, float* grad_pyramid, int64_t planes, int hs, int ws,
+                                    int extra_levels, void* stream);
+GG_API int gg_mipmap_warp_forward(void* out, float* levels_out, const void* src, const float* pyramid,
+                                  const float* grid, int dtype, int64_t N, int C, int hs, int ws, int ho,
+                                  int wo, int extra_levels, float max_level, float min_level,
+                                  int padding_mode, void* stream);
+GG_API int gg_mipmap_warp_backward(float* grad_src, float* grad_pyramid, float* grad_grid,
+                                   const void* grad_out, const void* src, const float* pyramid,
+                                   const float* grid, int dtype, int64_t N, int C, int hs, int ws, int ho,
+                                   int wo, int extra_levels, float max_level, float min_level,
+                                   int padding_mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flow composition of the flow STN head -- replaces upsample_flow + identity add + apply_affine + alpha lerp
+ *   reference: models/spatial_transformers/warping_heads.py:180-193 (RAFT convex upsampling: softmax over the
+ *   9 mask logits x F.unfold(S*flow, 3x3, padding=1)), :239-244, :268-277 (apply_affine: [gx, gy, 1] @ M^T)
+ *   low_flow (N, H, W, 2); mask (N, 9*S*S, H, W); identity_flow (S*H, S*W, 2) = F.affine_grid(identity);
+ *   base_warp (N, 2, 3) or NULL; alpha (N) or NULL.  All fp32.
+ *   forward : delta_flow (N, S*H, S*W, 2) and, if `flow` != NULL, flow = lerp(identity, affine(identity + delta), alpha)
+ *   backward: grad_mask (written), grad_low_flow and grad_base_warp (ZERO-INITIALISED by the caller,
+ *             accumulated with atomics); grad_delta / grad_flow are the incoming gradients (either may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int gg_flow_compose_forward(float* delta_flow, float* flow, const float* low_flow, const float* mask,
+                                   const float* identity_flow, const float* base_warp, const float* alpha,
+                                   int64_t N, int H, int W, int S, void* stream);
+GG_API int gg_flow_compose_backward(float* grad_mask, float* grad_low_flow, float* grad_base_warp,
+                                    const float* grad_delta, const float* grad_flow, const float* low_flow,
+                                    const float* mask, const float* identity_flow, const float* base_warp,
+                                    const float* alpha, int64_t N, int H, int W, int S, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * gg_splat2d_forward -- replaces `_splat.splat_forward_cuda(input, coordinates, values, sigma, soft_normalize)`
+ *   reference: utils/splat2d_cuda/src/splat_gpu.c:12-42 (host: zeros/clone/clamp/divide) and
+ *              splat_gpu_impl.cu:41-96 / splat_gpu_impl.cuh:11-22 (kernel `SplatForward`, extern-C `SplatForwardGpu`)
+ *   For every point (x, y) inside the image (0 <= x < W, 0 <= y < H) and every pixel of its footprint
+ *   [floor(y-2s), ceil(y+2s)] x [floor(x-2s), ceil(x+2s)] clipped to the image:
+ *       a = exp(-((px-x)^2 + (py-y)^2) / (2 s^2));  A[py,px] += a;  S[c,py,px] += a * value[c]
+ *   out = (input + S) / ((soft_normalize ? max(A, 1) : A) + 1e-8)
+ *   input/out (N, C, H, W); coordinates (N, P, 2) as (x, y); values (N, P, C); sigma (N).  fp32 only, forward
+ *   only (as the reference).  `workspace`: gg_splat2d_workspace() bytes (interleaved accumulators; the
+ *   library zeroes it).
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int64_t gg_splat2d_workspace(int64_t N, int C, int H, int W);
+GG_API int gg_splat2d_forward(float* out, void* workspace, const float* input, const float* coordinates,
+                              const float* values, const float* sigma, int64_t N, int64_t P, int C, int H,
+                              int W, int soft_normalize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

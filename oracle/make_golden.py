@@ -111,7 +111,119 @@ def main():
         extra(ref_models)
 
 
-EXTRA_GENERATORS = []
+def _smooth_grid(gen, n, res, theta, jitter):
+    import torch.nn.functional as F
+    base = F.affine_grid(theta, (n, 3, res, res), align_corners=False)
+    coarse = torch.randn(n, 2, 5, 5, generator=gen)
+    bump = F.interpolate(coarse, size=(res, res), mode="bicubic", align_corners=False).permute(0, 2, 3, 1)
+    return (base + jitter * bump).contiguous()
+
+
+WARP_CASES = [
+    # name, source size, output res, affine rows per sample, jitter, padding mode
+    ("minify_border", 32, 16, [[2.1, 0.4, 0.1, -0.4, 2.1, -0.2], [1.3, 0.0, 0.3, 0.0, 1.3, 0.0]], 0.00, "border"),
+    ("minify_reflect", 32, 16, [[2.1, 0.4, 0.1, -0.4, 2.1, -0.2], [3.3, 0.0, 0.3, 0.0, 3.3, 0.5]], 0.00, "reflection"),
+    ("minify_zeros", 32, 16, [[2.1, 0.4, 0.1, -0.4, 2.1, -0.2], [1.3, 0.0, 0.3, 0.0, 1.3, 0.0]], 0.00, "zeros"),
+    ("flow_border", 64, 64, [[1.0, 0.0, 0.0, 0.0, 1.0, 0.0], [1.6, 0.2, 0.0, -0.2, 1.6, 0.1]], 0.15, "border"),
+    ("flow_reflect", 64, 32, [[1.2, 0.0, 0.4, 0.0, 1.2, -0.3], [2.6, 0.2, 0.0, -0.2, 2.6, 0.1]], 0.20, "reflection"),
+    ("nonpow2_src", 20, 12, [[1.9, 0.1, 0.0, -0.1, 1.9, 0.0], [0.7, 0.0, 0.0, 0.0, 0.7, 0.1]], 0.05, "border"),
+    ("nonpow2_52", 52, 24, [[1.0, 0.0, 0.0, 0.0, 1.0, 0.0], [1.5, 0.5, 0.0, -0.5, 1.5, 0.0]], 0.02, "border"),
+    ("identity", 16, 16, [[1.0, 0.0, 0.0, 0.0, 1.0, 0.0], [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]], 0.00, "border"),
+]
+
+
+def gen_mipmap_warp(ref_models):
+    import torch.nn.functional as F
+    from models.spatial_transformers.antialiased_sampling import MipmapWarp, Warp, BilinearDownsample
+    from oracle import sampling as S
+    out = {}
+    for i, (name, size, res, rows, jitter, mode) in enumerate(WARP_CASES):
+        gen = torch.Generator().manual_seed(3000 + i)
+        x = torch.randn(2, 3, size, size, generator=gen, requires_grad=True)
+        theta = torch.tensor(rows).reshape(2, 2, 3)
+        grid = _smooth_grid(gen, 2, res, theta, jitter).requires_grad_(True)
+        go = torch.randn(2, 3, res, res, generator=gen)
+        mw = MipmapWarp(3.5)
+        y_ref = mw(x, grid, padding_mode=mode)
+        gx_ref, gg_ref = torch.autograd.grad(y_ref, [x, grid], go)
+        levels_ref = mw.levels_map * 2.5
+        # oracle restatement (explicit index arithmetic) against the reference, forward and autograd
+        xo, go_ = x.detach().clone().requires_grad_(True), grid.detach().clone().requires_grad_(True)
+        y_or, aux = S.mipmap_warp_ref(xo, go_, 3.5, 0.0, mode, return_aux=True)
+        gx_or, gg_or = torch.autograd.grad(y_or, [xo, go_], go)
+        _close(y_or, y_ref.detach(), 5e-6, "mipmap_warp/" + name)
+        _close(gx_or, gx_ref, 2e-5, "mipmap_warp gx/" + name)
+        _close(gg_or, gg_ref, 2e-4, "mipmap_warp ggrid/" + name)
+        assert torch.equal(aux["levels"], levels_ref.detach()) or (aux["levels"] - levels_ref).abs().max() < 1e-6
+        out[name + ".x"], out[name + ".grid"], out[name + ".go"] = x.detach(), grid.detach(), go
+        out[name + ".mode"] = np.array(S.PAD_MODES.index(mode))
+        out[name + ".y"], out[name + ".gx"], out[name + ".ggrid"] = y_ref.detach(), gx_ref, gg_ref
+        out[name + ".levels"] = aux["levels"]
+        # plain Warp on the same inputs
+        yw = Warp()(x, grid, padding_mode=mode)
+        gxw, ggw = torch.autograd.grad(yw, [x, grid], go)
+        _close(S.warp_ref(x.detach(), grid.detach(), mode), yw.detach(), 5e-6, "warp/" + name)
+        out[name + ".warp_y"], out[name + ".warp_gx"], out[name + ".warp_ggrid"] = yw.detach(), gxw, ggw
+    _save("mipmap_warp", **out)
+    # BilinearDownsample (resize_fake2stn, train.py:62)
+    gen = torch.Generator().manual_seed(3100)
+    x = torch.randn(2, 3, 32, 32, generator=gen)
+    bd = {}
+    for stride in (2, 4):
+        y = BilinearDownsample(stride, 3)(x)
+        _close(S.bilinear_downsample_ref(x, stride), y, 1e-6, "bilinear_downsample")
+        bd["s%d.y" % stride] = y
+    bd["x"] = x
+    _save("bilinear_downsample", **bd)
+
+
+def gen_flow(ref_models):
+    from models.spatial_transformers import warping_heads as wh
+    from oracle import flow as FL
+    out = {}
+
+    class _Head:  # FlowHead.__init__ calls .cuda() (warping_heads.py:158); its methods only need this attribute
+        flow_downsample = 8
+
+    for i, (n, h, w, s) in enumerate([(2, 4, 4, 8), (3, 6, 5, 4), (1, 8, 8, 8)]):
+        gen = torch.Generator().manual_seed(4000 + i)
+        _Head.flow_downsample = s
+        low = (0.05 * torch.randn(n, h, w, 2, generator=gen)).requires_grad_(True)
+        mask = torch.randn(n, 9 * s * s, h, w, generator=gen, requires_grad=True)
+        base = (torch.eye(2, 3)[None] + 0.2 * torch.randn(n, 2, 3, generator=gen)).requires_grad_(True)
+        ident = FL.identity_flow_ref(s * h, s * w)
+        delta_ref = wh.FlowHead.upsample_flow(_Head, low, mask)
+        flow_ref = wh.apply_affine(base, ident + delta_ref)
+        gd = torch.randn(delta_ref.shape, generator=gen)
+        gf = torch.randn(flow_ref.shape, generator=gen)
+        grads_ref = torch.autograd.grad((delta_ref * gd).sum() + (flow_ref * gf).sum(), [low, mask, base])
+        lo, mo, bo = [t.detach().clone().requires_grad_(True) for t in (low, mask, base)]
+        delta_or, flow_or = FL.flow_compose_ref(lo, mo, ident, bo, None, s)
+        grads_or = torch.autograd.grad((delta_or * gd).sum() + (flow_or * gf).sum(), [lo, mo, bo])
+        _close(delta_or, delta_ref.detach(), 1e-6, "upsample_flow %d" % i)
+        _close(flow_or, flow_ref.detach(), 1e-6, "apply_affine %d" % i)
+        for a, b, nm in zip(grads_or, grads_ref, ("low", "mask", "base")):
+            _close(a, b, 1e-5, "flow grads %s %d" % (nm, i))
+        tag = "case%d" % i
+        out[tag + ".low"], out[tag + ".mask"], out[tag + ".base"] = low.detach(), mask.detach(), base.detach()
+        out[tag + ".s"] = np.array(s)
+        out[tag + ".gd"], out[tag + ".gf"] = gd, gf
+        out[tag + ".delta"], out[tag + ".flow"] = delta_ref.detach(), flow_ref.detach()
+        out[tag + ".g_low"], out[tag + ".g_mask"], out[tag + ".g_base"] = grads_ref
+    # similarity matrices (SimilarityHead.make_affine_matrix / make_3x3)
+    gen = torch.Generator().manual_seed(4100)
+    params = torch.randn(5, 8, generator=gen)  # K = 2
+    m_ref = wh.SimilarityHead.make_affine_matrix(*torch.split(params, 2, dim=1))
+    _close(FL.similarity_matrix_ref(params), m_ref, 1e-6, "similarity matrix")
+    base = torch.randn(5, 2, 2, 3, generator=gen)
+    one_hot = torch.tensor([0, 0, 1], dtype=torch.float).view(1, 1, 1, 3).expand(5, 2, 1, 3)
+    comp_ref = base @ torch.cat([m_ref, one_hot], 2)
+    _close(FL.compose_similarity_ref(base, m_ref), comp_ref, 1e-6, "similarity compose")
+    out["sim.params"], out["sim.matrix"], out["sim.base"], out["sim.composed"] = params, m_ref, base, comp_ref
+    _save("flow_compose", **out)
+
+
+EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow]
 
 if __name__ == "__main__":
     main()
