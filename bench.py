@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""bench.py -- GANgealing train images/sec at 256^2 (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W              # this repo's sm_100a path
+  torchrun ... bench.py --gpus N --steps K --warmup W        # one rank per GPU, NCCL (the driver launches this)
+  python bench.py --impl reference ...                       # the reference algorithm on the host CPU cores
+
+A "step" is one full training iteration of BASELINE config 2 (LSUN-Cats-256 recipe: frozen StyleGAN2-256
+generator forward x2, similarity+flow STN @128, perceptual loss, backward, Adam x2, EMA, loss reduce) on a
+synthetic batch (seeded random weights, z ~ N(0,1); no datasets or checkpoints exist offline).
+Rank 0 prints ONE JSON line; see README / DESIGN.md for the field definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gangealing_train_images_per_sec_256"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("GG_BENCH_BATCH", "16")), help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def workload_config(args):
+    return {"workload": "LSUN Cats 256^2 train.py step (StyleGAN2-256 generator + unimodal similarity+flow STN @128, "
+                        "perceptual VGG16 loss, Adam, EMA), synthetic latents + seeded random weights",
+            "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "gen_size": 256, "flow_size": 128,
+            "parallelism": "dp%d" % args.gpus, "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB)"}
+
+
+# --------------------------------------------------------------------------------------------------- reference arm
+def cpu_step_rate(batch, steps=1, warmup=0):
+    """The reference algorithm (oracle port: same host code, CPU op set) on all host cores -> images/s."""
+    from oracle import opset
+    from gangealing_b200.training import TrainConfig, Trainer
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = TrainConfig(batch=batch)
+    tr = Trainer(cfg, "cpu", ops=opset.cpu_ops())
+    for _ in range(warmup):
+        tr.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = tr.step()
+    float(out["p"])
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    cores = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 2))  # bounded sample: each CPU step of B=2 takes ~10-20 s
+    warm = 1 if args.warmup > 0 else 0
+    rate, sec = cpu_step_rate(args.cpu_batch, steps=steps, warmup=warm)
+    sample = "%d step(s) of per-step batch %d (of the %d-per-GPU workload), %d host threads" % (steps, args.cpu_batch, args.batch, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from gangealing_b200 import _lib
+    from gangealing_b200.op import styled_tail
+    from gangealing_b200.training import TrainConfig, Trainer
+    from gangealing_b200.training import distributed as gdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        gdist.setup_distributed("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    rank = gdist.get_rank()
+    torch.backends.cudnn.benchmark = True
+
+    cfg = TrainConfig(batch=args.batch)
+    tr = Trainer(cfg, dev, distributed=distributed)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        tr.step()
+    sync_all()
+
+    # ---- timed region 1: device-resident inputs (latents drawn on the device, like reference loss.py:24)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    styled_tail.TIMING = []
+    calls0 = _lib.CALLS
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    st.record()
+    for _ in range(args.steps):
+        out = tr.step()
+    en.record()
+    sync_all()
+    ms = st.elapsed_time(en)
+    calls = _lib.CALLS - calls0
+    timing, styled_tail.TIMING = styled_tail.TIMING, None
+    if sampler:
+        sampler.stop_flag.set()
+
+    # ---- timed region 2: end to end through the public step() with HOST latents (pinned) and a host read of the loss
+    z_host = torch.randn(args.batch, cfg.dim_latent).pin_memory()
+    loss_host = torch.zeros(3).pin_memory()
+    sync_all()
+    st2, en2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st2.record()
+    for _ in range(args.steps):
+        z = z_host.to(dev, non_blocking=True)
+        out = tr.step(z)
+        loss_host.copy_(torch.stack([out["p"].detach().reshape(()), out["tv"].detach().reshape(()), out["f"].detach().reshape(())]))
+        torch.cuda.current_stream().synchronize()  # the host now holds this step's losses
+    en2.record()
+    sync_all()
+    ms2 = st2.elapsed_time(en2)
+
+    t = torch.tensor([ms, ms2], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms2 = t.tolist()
+    if rank != 0:
+        if distributed:
+            dist.barrier()
+        return
+
+    images = args.batch * world * args.steps
+    value = images / (ms / 1e3)
+    e2e = images / (ms2 / 1e3)
+    # roofline of the dominant hand-written kernel: the fused blur+noise+bias+act tail at the 256^2 layer
+    peak, peak_src = peaks()
+    roof = None
+    if timing:
+        biggest = max(t_[2] for t_ in timing)
+        sel = [t_ for t_ in timing if t_[2] == biggest]
+        durs = [a.elapsed_time(b) for a, b, _ in sel]
+        avg_ms = sum(durs) / len(durs)
+        achieved = biggest / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "fir4_band_kernel<float,*,FUSED> (blur+noise+bias+lrelu, 256^2 layer)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": biggest, "launches_timed": len(durs), "avg_launch_ms": avg_ms,
+                "peak_source": peak_src}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            rate, sec = cpu_step_rate(args.cpu_batch, steps=1, warmup=0)
+            cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": "1 step of per-step batch %d on %d host threads (%.1f s)" % (args.cpu_batch, os.cpu_count(), sec)}
+        except Exception as exc:  # the baseline must never take the bench down
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (exc,)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.batch * cfg.dim_latent * 4 * world,
+                    "d2h_bytes_per_step": 12 * world, "ms_per_step": ms2 / args.steps},
+            "gpu_launches": calls, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": sampler.summary() if sampler else None,
+            "losses": {k: float(v) for k, v in out.items()}}
+    print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,7 @@ SIGNATURES = {
 }
 
 _dll = None
+CALLS = 0  # C-ABI calls that launched device work (bench.py reports the count as gpu_launches; >= 1 kernel each)
 
 
 def load():
@@ -62,6 +63,8 @@ def load():
 
 
 def check(rc, what):
+    global CALLS
+    CALLS += 1
     if rc != 0:
         msg = load().gg_last_error().decode("utf-8", "replace")
         raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))

@@ -88,19 +88,22 @@ splat_scatter_kernel(float* __restrict__ acc, const float* __restrict__ coords, 
         s[0] = alpha;
 #pragma unroll
         for (int q = 1; q < GROUPS * 4; ++q) s[q] = alpha * v[q];
-        // segmented inclusive scan over runs of equal keys (contiguous duplicates)
+        // Merge CONTIGUOUS runs of lanes that hit the same pixel (rasterised point sets put duplicates next to each
+        // other): segmented inclusive scan bounded by the first lane of the run, then the run's last lane issues
+        // the reduction.  Non-adjacent duplicates simply issue their own reductions.
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const unsigned below = ~peers & ((1u << lane) - 1u);          // lanes below me that are NOT my pixel
+        const int run_start = below ? 32 - __clz(below) : 0;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const int64_t k2 = __shfl_up_sync(0xffffffffu, key, d);
-          const bool take = lane >= d && k2 == key;
+          const bool take = lane - d >= run_start;
 #pragma unroll
           for (int q = 0; q < GROUPS * 4; ++q) {
             const float up = __shfl_up_sync(0xffffffffu, s[q], d);
             if (take) s[q] += up;
           }
         }
-        const int64_t knext = __shfl_down_sync(0xffffffffu, key, 1);
-        const bool tail = ok && (lane == 31 || knext != key);
+        const bool tail = ok && (lane == 31 || !((peers >> (lane + 1)) & 1u));
         if (tail) {
           float* dst = acc_n + (static_cast<int64_t>(py) * p.w + px) * p.slots;
 #pragma unroll

@@ -100,16 +100,23 @@ constexpr int kBandWarps = kBandThreads / 32;
 constexpr int kStages = 3;
 constexpr int kRS = 8;   // output rows per lane (the register window slides over kRS + 3 input rows)
 constexpr int kCO = 4;   // adjacent output columns per lane (one 16-byte store for fp32)
-constexpr int kFrontBytes = 16;  // guard in front of every stage so column -1..-3 of the first staged row is addressable
+constexpr int kGuard = 16;  // bytes in front of every slot, so columns -1..-3 of its first row are addressable
 
+// A work item is `planes_per_item` consecutive planes x one band of output rows.  Each plane of the item owns a
+// SLOT of the stage that holds the band's VIRTUAL input rows vy0 .. vy0 + vrows - 1 (vy0 = oy0 - pad_y0, vrows =
+// band rows + 3) back to back at pitch in_w: the real rows arrive by one bulk-TMA copy of the 16-byte-aligned
+// superset of their contiguous global span; rows outside the image (zero padding above/below) and the few foreign
+// elements the aligned superset drags in are zero-filled by the CTA once the copy has landed.  Consumers therefore
+// never test row validity: every input of every output is a plain shared-memory read.
 struct BandParams {
   int64_t planes;        // M = N*C
   int in_h, in_w, out_h, out_w;
   int pad_x0, pad_y0;
   int band_rows;         // R: output rows per work item
-  int bands;             // ceil(out_h / R); when 1, an item may span several whole planes
-  int planes_per_item;   // P (1 unless bands == 1)
-  int stage_elems;       // shared-memory elements per stage
+  int bands;             // ceil(out_h / R)
+  int planes_per_item;   // P (> 1 only when bands == 1)
+  int slot_elems;        // elements per plane slot (multiple of 16 B)
+  int stage_elems;       // P * slot_elems
   int lx_log2;           // lanes across a strip = 1 << lx_log2 (strip = 4*lanes columns)
   int vec_io;            // 1: out (and noise) rows are 16-byte aligned -> vector store / load
   // fused epilogue
@@ -118,111 +125,121 @@ struct BandParams {
   float alpha, scale;
 };
 
-template <typename T>
-struct Span {            // contiguous input span of one work item
-  const T* src;          // 16-byte aligned start
-  uint32_t bytes;        // multiple of 16 (0: band sees only padding)
-  int shift;             // elements between src and the first needed element
-  int iy_lo;             // first staged input row (of the item's first plane)
+constexpr int kMaxPlanesPerItem = 32;
+
+struct Item {            // geometry shared by all planes of a work item
   int64_t m0;            // first plane
-  int n_planes;          // planes in this item
-  int n_rows_staged;     // staged input rows (single-plane items)
+  int n_planes;
   int oy0, rows;         // output rows of the band
+  int vy0, vrows;        // virtual input rows held by a slot
+  int lo, nreal;         // real input rows [lo, lo + nreal) (nreal <= 0: the band sees only padding)
+  int d0;                // element offset of the copy destination inside a slot (multiple of 16 B)
+};
+
+struct ItemS {           // what the producer thread publishes per stage (shared memory)
+  Item it;
+  int v0[kMaxPlanesPerItem];   // slot position of (virtual row vy0, column 0), per plane
+};
+
+__device__ __forceinline__ Item item_geom(const BandParams& p, int64_t item, int elem_size) {
+  Item it;
+  if (p.bands == 1) {
+    it.m0 = item * p.planes_per_item;
+    it.n_planes = static_cast<int>(min(static_cast<int64_t>(p.planes_per_item), p.planes - it.m0));
+    it.oy0 = 0;
+    it.rows = p.out_h;
+  } else {
+    it.m0 = item / p.bands;
+    it.n_planes = 1;
+    it.oy0 = static_cast<int>(item - it.m0 * p.bands) * p.band_rows;
+    it.rows = min(p.band_rows, p.out_h - it.oy0);
+  }
+  it.vy0 = it.oy0 - p.pad_y0;
+  it.vrows = it.rows + 3;
+  it.lo = max(it.vy0, 0);
+  const int hi = min(it.vy0 + it.vrows - 1, p.in_h - 1);
+  it.nreal = hi - it.lo + 1;
+  const int per16 = 16 / elem_size;
+  const int n_top = (it.nreal > 0 ? it.lo : it.vy0 + it.vrows) - it.vy0;   // zero rows above the first real row
+  it.d0 = (kGuard / elem_size + n_top * p.in_w + per16 - 1) / per16 * per16;
+  return it;
+}
+
+template <typename T>
+struct PlaneCopy {       // bulk copy of one plane's real rows
+  const T* src;          // 16-byte aligned
+  uint32_t bytes;        // multiple of 16
+  int shift;             // elements between src and the first real element
 };
 
 template <typename T>
-__device__ __forceinline__ Span<T> item_span(const T* in, const BandParams& p, int64_t item) {
-  Span<T> s;
-  if (p.bands == 1) {
-    s.m0 = item * p.planes_per_item;
-    s.n_planes = static_cast<int>(min(static_cast<int64_t>(p.planes_per_item), p.planes - s.m0));
-    s.oy0 = 0;
-    s.rows = p.out_h;
-  } else {
-    s.m0 = item / p.bands;
-    s.n_planes = 1;
-    s.oy0 = static_cast<int>(item - s.m0 * p.bands) * p.band_rows;
-    s.rows = min(p.band_rows, p.out_h - s.oy0);
-  }
-  int lo, hi;
-  if (s.n_planes > 1) {  // whole planes, back to back
-    lo = 0; hi = p.in_h - 1;
-  } else {
-    lo = max(s.oy0 - p.pad_y0, 0);
-    hi = min(s.oy0 + s.rows - 1 + 3 - p.pad_y0, p.in_h - 1);
-  }
-  s.iy_lo = lo;
-  s.n_rows_staged = hi - lo + 1;
-  if (hi < lo) {
-    s.src = in; s.bytes = 0; s.shift = 0;
-    return s;
-  }
-  const T* first = in + (s.m0 * p.in_h + lo) * static_cast<int64_t>(p.in_w);
-  const T* last = in + ((s.m0 + s.n_planes - 1) * p.in_h + hi + 1) * static_cast<int64_t>(p.in_w);  // one past
+__device__ __forceinline__ PlaneCopy<T> plane_copy(const T* in, const BandParams& p, const Item& it, int pl) {
+  PlaneCopy<T> c;
+  const T* first = in + ((it.m0 + pl) * p.in_h + it.lo) * static_cast<int64_t>(p.in_w);
+  const T* last = first + static_cast<int64_t>(it.nreal) * p.in_w;  // one past
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(first) & ~static_cast<uintptr_t>(15);
   const uintptr_t a1 = (reinterpret_cast<uintptr_t>(last) + 15) & ~static_cast<uintptr_t>(15);
-  s.src = reinterpret_cast<const T*>(a0);
-  s.bytes = static_cast<uint32_t>(a1 - a0);
-  s.shift = static_cast<int>((reinterpret_cast<uintptr_t>(first) - a0) / sizeof(T));
-  return s;
+  c.src = reinterpret_cast<const T*>(a0);
+  c.bytes = static_cast<uint32_t>(a1 - a0);
+  c.shift = static_cast<int>((reinterpret_cast<uintptr_t>(first) - a0) / sizeof(T));
+  return c;
+}
+
+// issued by one thread: publish the item's geometry, arm the barrier with the item's total bytes, then one
+// bulk copy per plane
+template <typename T>
+__device__ __forceinline__ void issue_item(const T* in, const BandParams& p, int64_t item, T* stage, uint64_t* bar,
+                                           ItemS* pub) {
+  const Item it = item_geom(p, item, sizeof(T));
+  pub->it = it;
+  if (it.nreal <= 0) {
+    for (int pl = 0; pl < it.n_planes; ++pl) pub->v0[pl] = it.d0 - it.vrows * p.in_w;
+    return;
+  }
+  uint32_t total = 0;
+  for (int pl = 0; pl < it.n_planes; ++pl) {
+    const PlaneCopy<T> c = plane_copy(in, p, it, pl);
+    total += c.bytes;
+    pub->v0[pl] = it.d0 + c.shift - (it.lo - it.vy0) * p.in_w;
+  }
+  // the stage was last touched through the generic proxy (zero-fill stores, reads): order them before the
+  // async-proxy writes of the copies
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(bar, total);
+  for (int pl = 0; pl < it.n_planes; ++pl) {
+    const PlaneCopy<T> c = plane_copy(in, p, it, pl);
+    tma_bulk_g2s(stage + static_cast<int64_t>(pl) * p.slot_elems + it.d0, c.src, c.bytes, bar);
+  }
 }
 
 template <typename T> struct Vec4 { T v[4]; };
 
-// One lane: 4 adjacent output columns x up to kRS output rows of one plane, register window sliding down.
-// SEP: the filter is an outer product u (rows) x v (columns): horizontal pass once per input row, vertical
-// pass over a 4-row window of horizontal results (8 FMA/output instead of 16).
+// Generic-type lane (any T, separable or full 16-tap filter): 4 adjacent output columns x up to kRS rows with a
+// register window sliding down.  `vrow0` points at virtual row vy0, column 0 of this plane's slot.
 template <typename T, bool SEP, bool FUSED>
-__device__ __forceinline__ void lane_strip(T* __restrict__ out_plane, const T* __restrict__ tile_plane,
+__device__ __forceinline__ void lane_strip(T* __restrict__ out_plane, const T* __restrict__ vrow0, int vy0,
                                            const T* __restrict__ noise_plane, const BandParams& p,
                                            const float (&kf)[4][4], const float (&ku)[4], const float (&kv)[4],
-                                           int oys, int nrow, int x0, int iy_lo, float rs, float bc, float nw) {
-  // tile_plane points at staged row iy_lo of this plane; output rows [oys, oys + nrow), columns [x0, x0 + 4)
+                                           int oys, int nrow, int x0, float rs, float bc, float nw) {
   const int colbase = x0 - p.pad_x0;
   int cidx[kCO + 3];
   uint32_t cmask[kCO + 3];
 #pragma unroll
   for (int i = 0; i < kCO + 3; ++i) {
     const int c = colbase + i;
-    const bool ok = (c >= 0) && (c < p.in_w);
     cidx[i] = min(max(c, 0), p.in_w - 1);
-    cmask[i] = ok ? 0xffffffffu : 0u;
+    cmask[i] = (c >= 0 && c < p.in_w) ? 0xffffffffu : 0u;
   }
   const int iys = oys - p.pad_y0;
-
-  // separable path: all noise rows of the strip are fetched up front (latency fully hidden behind the
-  // window warm-up); the 16-tap path needs its registers for the raw window and loads them at use
-  Vec4<T> nz[SEP ? kRS : 1];
-  if (SEP && FUSED && noise_plane) {
-#pragma unroll
-    for (int r = 0; r < kRS; ++r) {
-      if (r < nrow) {
-        const T* np_ = noise_plane + static_cast<int64_t>(oys + r) * p.out_w + x0;
-        if (p.vec_io) {
-          nz[r] = *reinterpret_cast<const Vec4<T>*>(np_);
-        } else {
-#pragma unroll
-          for (int j = 0; j < kCO; ++j) nz[r].v[j] = (x0 + j < p.out_w) ? np_[j] : Cvt<T>::from_f(0.f);
-        }
-      }
-    }
-  }
-
   float win[4][SEP ? kCO : kCO + 3];
 #pragma unroll
   for (int r = 0; r < kRS + 3; ++r) {
     if (r < nrow + 3) {
-      const int iy = iys + r;
+      const T* trow = vrow0 + static_cast<int64_t>(iys + r - vy0) * p.in_w;
       float raw[kCO + 3];
-      if (iy >= 0 && iy < p.in_h) {
-        const T* trow = tile_plane + static_cast<int64_t>(iy - iy_lo) * p.in_w;
 #pragma unroll
-        for (int i = 0; i < kCO + 3; ++i)
-          raw[i] = __uint_as_float(__float_as_uint(Cvt<T>::to_f(trow[cidx[i]])) & cmask[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < kCO + 3; ++i) raw[i] = 0.f;
-      }
+      for (int i = 0; i < kCO + 3; ++i)
+        raw[i] = __uint_as_float(__float_as_uint(Cvt<T>::to_f(trow[cidx[i]])) & cmask[i]);
       if (SEP) {
 #pragma unroll
         for (int j = 0; j < kCO; ++j)
@@ -249,13 +266,8 @@ __device__ __forceinline__ void lane_strip(T* __restrict__ out_plane, const T* _
           }
           if (FUSED) {
             float t = fmaf(acc[j], rs, bc);
-            if (noise_plane) {
-              const float nv = SEP ? Cvt<T>::to_f(nz[SEP ? ro : 0].v[j])
-                                   : ((x0 + j < p.out_w)
-                                          ? Cvt<T>::to_f(noise_plane[static_cast<int64_t>(oys + ro) * p.out_w + x0 + j])
-                                          : 0.f);
-              t = fmaf(nw, nv, t);
-            }
+            if (noise_plane && x0 + j < p.out_w)
+              t = fmaf(nw, Cvt<T>::to_f(noise_plane[static_cast<int64_t>(oys + ro) * p.out_w + x0 + j]), t);
             const float g = (p.act == 3 && t < 0.f) ? p.alpha * p.scale : p.scale;
             acc[j] = t * g;
           }
@@ -276,48 +288,40 @@ __device__ __forceinline__ void lane_strip(T* __restrict__ out_plane, const T* _
   }
 }
 
-// fp32 + separable filter fast path.  The stage holds the span as one flat array, so element (row, col) sits at
-// flat position pos = row*in_w + col + const, whose 16-byte alignment rotates from row to row (in_w is odd on
+// fp32 + separable filter fast path.  A slot holds its virtual rows as one flat array, so element (row, col) sits
+// at flat position pos = row*in_w + col + const, whose 16-byte alignment rotates from row to row (in_w is odd on
 // the hot path).  Each lane reads the 16-byte-aligned quads covering its 7 inputs (LDS.128, consecutive lanes ->
 // consecutive quads: conflict-free).  Which registers feed the horizontal pass depends on pos mod 4, which is
 // WARP-UNIFORM and, given the alignment S0 of the strip's first row and IW4 = in_w mod 4, a compile-time
-// constant per unrolled row: the kernel is instantiated per IW4 and branches once per task on S0, so the
-// inner loop has no shuffles, selects or per-value address arithmetic.
-// Out-of-range columns are handled by folding a 0/1 mask into per-lane horizontal weights.
+// constant per unrolled row: the kernel is instantiated per IW4 and branches once per task on S0, so the inner
+// loop is straight-line FMA code: no row/column tests, shuffles, selects or per-value address arithmetic.
+// Out-of-range columns are handled by folding a 0/1 mask into per-lane horizontal weights (the elements they
+// touch are real neighbours or zero-filled guards, hence finite).
 template <int IW4, int S0, bool FUSED, bool VEC>
 struct StripF32 {
   float* __restrict__ out_ptr;        // &out[plane][oys][x0]
-  const float* __restrict__ stage;
+  const float* __restrict__ row_ptr;  // slot element (row oys - pad_y0, column x0 - pad_x0), NOT aligned
   const BandParams& p;
   const float (&ku)[4];
   float wgt[kCO][4];
   float4 nz[kRS];
   float hw[4][kCO];
-  int pos0, iys, nrow, x0;
-  float rs, bc, nw, gpos, gneg;
+  int nrow, x0;
+  float rs, bc, nw, gpos, gdiff;
   bool has_noise;
 
-  // Straight-line per-row step: no data-dependent branches.  Rows outside the image (zero padding) load from a
-  // safe aligned address and are zeroed by selects; rows past the strip's last output only feed outputs that
-  // are never stored.
   template <int R>
   __device__ __forceinline__ void step() {
-    const int iy = iys + R;
-    const bool rv = (iy >= 0) && (iy < p.in_h);
     constexpr int SH = (S0 + R * IW4) & 3;       // alignment of this row's first input (compile-time)
-    const float* a = stage + (pos0 + R * p.in_w - SH);
-    a = rv ? a : stage;
-    const float4* qp = reinterpret_cast<const float4*>(a);
+    const float4* qp = reinterpret_cast<const float4*>(row_ptr + R * p.in_w - SH);
     const float4 q0 = qp[0], q1 = qp[1];
     float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (SH >= 2) q2 = qp[2];                     // inputs SH .. SH+6 reach the third quad only when SH >= 2
     const float Q[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
-    for (int j = 0; j < kCO; ++j) {
-      const float h = fmaf(wgt[j][3], Q[SH + j + 3],
-                           fmaf(wgt[j][2], Q[SH + j + 2], fmaf(wgt[j][1], Q[SH + j + 1], wgt[j][0] * Q[SH + j])));
-      hw[R & 3][j] = rv ? h : 0.f;
-    }
+    for (int j = 0; j < kCO; ++j)
+      hw[R & 3][j] = fmaf(wgt[j][3], Q[SH + j + 3],
+                          fmaf(wgt[j][2], Q[SH + j + 2], fmaf(wgt[j][1], Q[SH + j + 1], wgt[j][0] * Q[SH + j])));
     if (R >= 3) {
       constexpr int RO = R >= 3 ? R - 3 : 0;
       float acc[kCO];
@@ -332,7 +336,8 @@ struct StripF32 {
             const float nv = j == 0 ? nv4.x : (j == 1 ? nv4.y : (j == 2 ? nv4.z : nv4.w));
             t = fmaf(nw, nv, t);
           }
-          acc[j] = t * (t < 0.f ? gneg : gpos);
+          // lrelu(t)*scale = scale*t + (alpha*scale - scale)*min(t, 0): one ALU op + two FMA-pipe ops
+          acc[j] = fmaf(gdiff, fminf(t, 0.f), gpos * t);
         }
       }
       if (RO < nrow) {
@@ -355,15 +360,14 @@ struct StripF32 {
 };
 
 template <int IW4, int S0, bool FUSED, bool VEC>
-__device__ __forceinline__ void lane_strip_f32(float* __restrict__ out_plane, const float* __restrict__ stage,
-                                               int pos0, const float* __restrict__ noise_plane, const BandParams& p,
+__device__ __forceinline__ void lane_strip_f32(float* __restrict__ out_plane, const float* __restrict__ row_ptr,
+                                               const float* __restrict__ noise_plane, const BandParams& p,
                                                const float (&ku)[4], const float (&kv)[4], int oys, int nrow, int x0,
                                                float rs, float bc, float nw) {
-  // pos0: flat position (elements from the 16-byte-aligned `stage`) of input (row oys - pad_y0, column x0 - pad_x0)
-  StripF32<IW4, S0, FUSED, VEC> st{out_plane + static_cast<int64_t>(oys) * p.out_w + x0, stage, p, ku};
-  st.pos0 = pos0; st.iys = oys - p.pad_y0; st.nrow = nrow; st.x0 = x0;
+  StripF32<IW4, S0, FUSED, VEC> st{out_plane + static_cast<int64_t>(oys) * p.out_w + x0, row_ptr, p, ku};
+  st.nrow = nrow; st.x0 = x0;
   st.rs = rs; st.bc = bc; st.nw = nw; st.has_noise = FUSED && noise_plane != nullptr;
-  st.gpos = p.scale; st.gneg = (p.act == 3) ? p.alpha * p.scale : p.scale;
+  st.gpos = p.scale; st.gdiff = (p.act == 3) ? p.alpha * p.scale - p.scale : 0.f;
   const int colbase = x0 - p.pad_x0;
 #pragma unroll
   for (int j = 0; j < kCO; ++j)
@@ -400,6 +404,7 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
                  const __grid_constant__ BandParams p, int64_t n_items) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[kStages];
+  __shared__ ItemS pub[kStages];
   T* stage_base = reinterpret_cast<T*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -417,14 +422,7 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
       const int64_t it = blockIdx.x + s * stride;
-      if (it < n_items) {
-        const Span<T> sp = item_span(in, p, it);
-        if (sp.bytes) {
-          mbar_expect_tx(&full_bar[s], sp.bytes);
-          tma_bulk_g2s(stage_base + static_cast<int64_t>(s) * p.stage_elems + kFrontBytes / sizeof(T), sp.src, sp.bytes,
-                       &full_bar[s]);
-        }
-      }
+      if (it < n_items) issue_item(in, p, it, stage_base + static_cast<int64_t>(s) * p.stage_elems, &full_bar[s], &pub[s]);
     }
   }
 
@@ -478,6 +476,7 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
 
   float nw = 0.f;
   if (FUSED) nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
+  __syncthreads();  // the prologue's published item geometry is visible to every thread
 
   // strip geometry: `full_x` strips of lx lanes x 4 columns, plus one narrower tail strip whose lanes
   // are folded down the rows instead (so 129- or 65-wide outputs do not pay for a second full strip)
@@ -496,37 +495,36 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
       const int64_t nxt = item + (kStages - 1) * stride;
       if (nxt < n_items) {
         const int ns = (k + kStages - 1) % kStages;
-        const Span<T> sp = item_span(in, p, nxt);
-        if (sp.bytes) {
-          mbar_expect_tx(&full_bar[ns], sp.bytes);
-          tma_bulk_g2s(stage_base + static_cast<int64_t>(ns) * p.stage_elems + kFrontBytes / sizeof(T), sp.src, sp.bytes,
-                       &full_bar[ns]);
-        }
+        issue_item(in, p, nxt, stage_base + static_cast<int64_t>(ns) * p.stage_elems, &full_bar[ns], &pub[ns]);
       }
     }
-    const Span<T> sp = item_span(in, p, item);
-    if (sp.bytes) {  // a padding-only band issues no transfer, so its stage's phase does not advance
+    // geometry published by the producer (visible: written before the previous iteration's / the prologue's barrier)
+    const Item& it = pub[stage].it;
+    if (it.nreal > 0) {  // a padding-only band issues no transfer, so its stage's phase does not advance
       mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
       phase_bits ^= 1u << stage;
     }
     T* stage_ptr = stage_base + static_cast<int64_t>(stage) * p.stage_elems;   // 16-byte aligned
-    const int tile_off = static_cast<int>(kFrontBytes / sizeof(T)) + sp.shift;     // staged row iy_lo, column 0
-    const T* tile = stage_ptr + tile_off;
-    if (sp.bytes) {
-      // The aligned superset drags in up to 3 foreign elements on either side of the span; zero-weight taps of
-      // edge lanes touch them (mask-folded weights), so make them finite zeros.  (Visible after the barrier.)
-      const int span_elems = static_cast<int>((sp.n_planes > 1 ? static_cast<int64_t>(sp.n_planes) * p.in_h
-                                                                : static_cast<int64_t>(sp.n_rows_staged)) * p.in_w);
-      if (tid < 3) stage_ptr[tile_off - 1 - tid] = Cvt<T>::from_f(0.f);
-      else if (tid < 6) stage_ptr[tile_off + span_elems + (tid - 3)] = Cvt<T>::from_f(0.f);
+    // zero padding rows above / below the image (first / last band of a plane only)
+    const int n_top = it.nreal > 0 ? it.lo - it.vy0 : it.vrows;
+    const int n_bot = it.nreal > 0 ? it.vrows - n_top - it.nreal : 0;
+    if (n_top > 0 || n_bot > 0) {
+      for (int pl = 0; pl < it.n_planes; ++pl) {
+        T* slot = stage_ptr + static_cast<int64_t>(pl) * p.slot_elems;
+        const int v0 = pub[stage].v0[pl];
+        const int first_real = v0 + n_top * p.in_w;
+        const int after_real = first_real + max(it.nreal, 0) * p.in_w;
+        for (int e = v0 + tid; e < first_real; e += kBandThreads) slot[e] = Cvt<T>::from_f(0.f);
+        for (int e = after_real + tid; e < v0 + it.vrows * p.in_w; e += kBandThreads) slot[e] = Cvt<T>::from_f(0.f);
+      }
+      __syncthreads();
     }
-    __syncthreads();
 
-    const int sy_main = (sp.rows + (32 >> p.lx_log2) * kRS - 1) / ((32 >> p.lx_log2) * kRS);
+    const int sy_main = (it.rows + (32 >> p.lx_log2) * kRS - 1) / ((32 >> p.lx_log2) * kRS);
     const int main_tasks = full_x * sy_main;
-    const int tail_tasks = tail_w > 0 ? (sp.rows + (32 >> lt_log2) * kRS - 1) / ((32 >> lt_log2) * kRS) : 0;
+    const int tail_tasks = tail_w > 0 ? (it.rows + (32 >> lt_log2) * kRS - 1) / ((32 >> lt_log2) * kRS) : 0;
     const int tasks_per_plane = main_tasks + tail_tasks;
-    const int n_tasks = tasks_per_plane * sp.n_planes;
+    const int n_tasks = tasks_per_plane * it.n_planes;
     for (int task = warp; task < n_tasks; task += kBandWarps) {
       const int pl = task / tasks_per_plane;
       const int rem = task - pl * tasks_per_plane;
@@ -542,9 +540,9 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
       }
       const int lane_x = lane & ((1 << lg) - 1);
       const int lane_y = lane >> lg;
-      const int64_t m = sp.m0 + pl;
-      const int oys = sp.oy0 + (sy * (32 >> lg) + lane_y) * kRS;
-      const int nrow = min(kRS, sp.oy0 + sp.rows - oys);
+      const int64_t m = it.m0 + pl;
+      const int oys = it.oy0 + (sy * (32 >> lg) + lane_y) * kRS;
+      const int nrow = min(kRS, it.oy0 + it.rows - oys);
       const int x0 = xs + lane_x * kCO;
       if (nrow <= 0 || x0 >= p.out_w) continue;
       float rs = 1.f, bc = 0.f;
@@ -557,13 +555,26 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
         if (noise) noise_plane = noise + n * p.out_h * static_cast<int64_t>(p.out_w);
       }
       T* out_plane = out + m * p.out_h * static_cast<int64_t>(p.out_w);
-      const T* tile_plane = tile + static_cast<int64_t>(pl) * p.in_h * p.in_w;
+      T* slot = stage_ptr + static_cast<int64_t>(pl) * p.slot_elems;
+      const int v0 = pub[stage].v0[pl];
+      // The 3 elements in front of the first virtual row and behind the last one are foreign (alignment
+      // prefix / suffix of the copy, or never written): only the lanes below ever touch them (with zero
+      // weight), so those lanes make them finite zeros themselves -- no extra barrier.
+      if (x0 == 0 && oys == it.oy0) {
+#pragma unroll
+        for (int e = 1; e <= 3; ++e) slot[v0 - e] = Cvt<T>::from_f(0.f);
+      }
+      if (x0 + kCO + 3 - p.pad_x0 > p.in_w && oys + kRS >= it.oy0 + it.rows) {
+        const int vend = v0 + it.vrows * p.in_w;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) slot[vend + e] = Cvt<T>::from_f(0.f);
+      }
       if constexpr (sizeof(T) == 4 && IW4 >= 0) {
         if (sep) {
-          const int pos0 = tile_off + (pl * p.in_h + (oys - p.pad_y0 - sp.iy_lo)) * p.in_w + (x0 - p.pad_x0);
+          const int pos0 = v0 + (oys - p.pad_y0 - it.vy0) * p.in_w + (x0 - p.pad_x0);
+          const float* row_ptr = reinterpret_cast<const float*>(slot) + pos0;
 #define GG_STRIP(S0_, V_)                                                                                    \
-  lane_strip_f32<IW4, S0_, FUSED, V_>(reinterpret_cast<float*>(out_plane),                                      \
-                                      reinterpret_cast<const float*>(stage_ptr), pos0,                          \
+  lane_strip_f32<IW4, S0_, FUSED, V_>(reinterpret_cast<float*>(out_plane), row_ptr,                             \
                                       reinterpret_cast<const float*>(noise_plane), p, ku, kv, oys, nrow, x0, rs, \
                                       bc, nw)
           if (p.vec_io) {
@@ -586,11 +597,11 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
         }
       }
       if (sep)
-        lane_strip<T, true, FUSED>(out_plane, tile_plane, noise_plane, p, kf, ku, kv, oys, nrow, x0, sp.iy_lo, rs, bc, nw);
+        lane_strip<T, true, FUSED>(out_plane, slot + v0, it.vy0, noise_plane, p, kf, ku, kv, oys, nrow, x0, rs, bc, nw);
       else
-        lane_strip<T, false, FUSED>(out_plane, tile_plane, noise_plane, p, kf, ku, kv, oys, nrow, x0, sp.iy_lo, rs, bc, nw);
+        lane_strip<T, false, FUSED>(out_plane, slot + v0, it.vy0, noise_plane, p, kf, ku, kv, oys, nrow, x0, rs, bc, nw);
     }
-    __syncthreads();  // every warp is done with `stage` before it is refilled next iteration
+    __syncthreads();  // every warp is done with `stage` (and its published geometry) before it is refilled
   }
 }
 
@@ -608,43 +619,47 @@ inline bool plan_band(int dtype, int64_t planes, int in_h, int in_w, int out_h, 
                       int pad_y0, const void* out, const void* noise, BandPlan* plan) {
   if (out_w < 24 || out_h < 8) return false;  // tiny planes: launch-bound, one thread per output is as good
   const int es = dtype_size(dtype);
-  const int slack = 32 / es;  // alignment shift (<16 B) + tail round-up (<16 B)
+  const int per16 = 16 / es;
   int lx_log2 = 5;
   while (lx_log2 > 0 && (1 << (lx_log2 - 1)) * kCO >= out_w) --lx_log2;
   const int lx = 1 << lx_log2, ly = 32 >> lx_log2;
   const int strip_w = lx * kCO, strip_h = ly * kRS;
   const int strips_x = out_w / strip_w > 0 ? out_w / strip_w : 1;  // full strips (the tail strip folds down the rows)
   const int64_t budget = 36 * 1024;  // bytes per stage (3 stages x 2 CTAs per SM)
-  const int64_t plane_bytes = static_cast<int64_t>(in_h) * in_w * es;
+  auto slot_elems_for = [&](int rows) {   // guard + virtual rows + alignment slack + trailing guard, 16-byte multiple
+    // a partial last strip still walks kRS + 3 input rows (its surplus outputs are never stored): round rows up
+    const int rows8 = (rows + kRS - 1) / kRS * kRS;
+    const int64_t e = kGuard / es + static_cast<int64_t>(rows8 + 3) * in_w + 2 * per16 + 4;
+    return (e + per16 - 1) / per16 * per16;
+  };
   BandParams& p = plan->p;
   int r, bands, ppi = 1;
-  if (plane_bytes <= budget) {           // whole planes per item, several when small
+  if (slot_elems_for(out_h) * es <= budget) {           // whole planes per item, several when small
     r = out_h; bands = 1;
-    // enough planes to give every warp a task, within the budget
     const int strips_y = (out_h + strip_h - 1) / strip_h;
     const int tasks = strips_x * strips_y;
     ppi = (kBandWarps + tasks - 1) / tasks;
-    const int64_t fit = budget / plane_bytes;
+    const int64_t fit = budget / (slot_elems_for(out_h) * es);
     if (ppi > fit) ppi = static_cast<int>(fit);
     if (ppi < 1) ppi = 1;
     if (ppi > planes) ppi = static_cast<int>(planes);
+    if (ppi > kMaxPlanesPerItem) ppi = kMaxPlanesPerItem;
   } else {
     // warp tasks per band: strips_x * R/strip_h; aim for >= 8 tasks within the budget
     r = strip_h * ((kBandWarps + strips_x - 1) / strips_x);
-    while (r > strip_h && static_cast<int64_t>(r + 3) * in_w * es > budget) r -= strip_h;
-    if (static_cast<int64_t>(r + 3) * in_w * es > 64 * 1024) return false;  // rows too wide for the ring
-    if (r >= out_h) { r = out_h; }
+    while (r > strip_h && slot_elems_for(r) * es > budget) r -= strip_h;
+    if (slot_elems_for(r) * es > 64 * 1024) return false;  // rows too wide for the ring
+    if (r >= out_h) return false;
     bands = (out_h + r - 1) / r;
-    if (bands == 1) return false;  // cannot happen with plane_bytes > budget unless pads are huge
   }
-  const int64_t rows_staged = (bands == 1) ? static_cast<int64_t>(ppi) * in_h : (r + 3);
-  const int64_t stage_elems = (rows_staged * in_w + slack + kFrontBytes / es + 16 / es + 15) / 16 * 16;
-  const size_t smem = static_cast<size_t>(stage_elems) * es * kStages;
+  const int64_t slot_elems = slot_elems_for(r);
+  const size_t smem = static_cast<size_t>(slot_elems) * ppi * es * kStages;
   if (smem > 200 * 1024) return false;
   p.planes = planes; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
   p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
   p.band_rows = r; p.bands = bands; p.planes_per_item = ppi;
-  p.stage_elems = static_cast<int>(stage_elems);
+  p.slot_elems = static_cast<int>(slot_elems);
+  p.stage_elems = static_cast<int>(slot_elems * ppi);
   p.lx_log2 = lx_log2;
   const uintptr_t align = static_cast<uintptr_t>(4 * es);
   p.vec_io = (out_w % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % align == 0) &&
@@ -654,7 +669,13 @@ inline bool plan_band(int dtype, int64_t planes, int in_h, int in_w, int out_h, 
   plan->n_items = (bands == 1) ? (planes + ppi - 1) / ppi : planes * bands;
   const int ctas_per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
   const int64_t max_grid = static_cast<int64_t>(sm_count()) * ctas_per_sm;
-  plan->grid = static_cast<int>(plan->n_items < max_grid ? plan->n_items : max_grid);
+  int64_t grid = plan->n_items < max_grid ? plan->n_items : max_grid;
+  // The fp32 fast path has one code variant per 16-byte alignment class of a plane's rows.  A persistent CTA strides
+  // over items by gridDim.x; rounding the grid down so that the stride is a whole number of 4 planes keeps every CTA
+  // on ONE alignment class, i.e. one hot code variant in its instruction cache instead of a rotation of four.
+  const int64_t unit = static_cast<int64_t>(bands) * 4;
+  if (grid >= 2 * unit) grid = grid / unit * unit;
+  plan->grid = static_cast<int>(grid);
   return true;
 }
 

@@ -14,6 +14,11 @@ from .fused_act import bias_act_backward_raw
 from .upfirdn2d import UpFirDn2d, _taps, grad_pad
 
 
+# bench.py sets this to a list to time every fused-blur launch with CUDA events on the launching stream:
+# entries are (start_event, end_event, algorithmic_bytes).  None (default): no instrumentation.
+TIMING = None
+
+
 def _f32(t):
     if t is None:
         return None
@@ -57,11 +62,20 @@ class _StyledTail(Function):
             out_w = in_w + pad[0] + pad[1] - kw + 1
             out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device)
             nz = _noise_plane(noise, x, out_h, out_w)
+            if TIMING is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             rc = lib.gg_blur_noise_bias_act(out.data_ptr(), x.data_ptr(), taps.data_ptr(), _lib.ptr(nz),
                                             _lib.ptr(nw), _lib.ptr(b), _lib.ptr(rs), _lib.dtype_code(x), n, c,
                                             in_h, in_w, kh, kw, pad[0], pad[1], pad[2], pad[3], 3,
                                             negative_slope, scale, _lib.stream())
             _lib.check(rc, "gg_blur_noise_bias_act")
+            if TIMING is not None:
+                ev1.record()
+                es = x.element_size()
+                nbytes = es * n * c * (in_h * in_w + out_h * out_w) + (es * n * out_h * out_w if nz is not None else 0) \
+                    + 4 * (c + 1 + kh * kw)
+                TIMING.append((ev0, ev1, nbytes))
         ctx.save_for_backward(out, noise, noise_weight, kernel, row_scale, x if row_scale is not None else None)
         ctx.cfg = (pad, negative_slope, scale, tuple(x.shape))
         return out

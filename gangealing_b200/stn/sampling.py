@@ -98,23 +98,57 @@ def _pad_code(padding_mode):
         raise RuntimeError("padding_mode must be 'zeros', 'border' or 'reflection', got %r" % (padding_mode,))
 
 
+def mipmap_warp(inputs, grid, max_num_levels=8, min_level=0.0, padding_mode="border"):
+    """Functional form of MipmapWarp.forward: -> (outputs, levels (N, Ho, Wo) fp32)."""
+    max_level = float(max_num_levels) - 1.0
+    wanted = int(math.ceil(max(max_level, float(min_level), 0.0)))
+    extra = feasible_levels(inputs.shape[2], inputs.shape[3], wanted)
+    if extra < wanted:  # tiny source: the reference only fails if such a level is actually selected
+        max_level = min(max_level, float(extra))
+        min_level = min(float(min_level), float(extra))
+    out, levels = _MipmapWarp.apply(inputs, grid, max_level, float(min_level), _pad_code(padding_mode), extra)
+    if extra == 0:
+        levels = torch.zeros(grid.shape[:3], device=grid.device)
+    return out, levels
+
+
+def bilinear_downsample(input, stride, kernel_horz, kernel_vert):
+    """Functional form of BilinearDownsample.forward (reflect-pad + separable tent filter with stride)."""
+    channels = input.shape[1]
+    pad = int(stride / 2)
+    x = F.pad(input, (pad, pad, pad, pad), mode="reflect")
+    rows = F.conv2d(x, kernel_horz, stride=(1, stride), groups=channels)
+    return F.conv2d(rows, kernel_vert, stride=(stride, 1), groups=channels)
+
+
 def grid_sample_bilinear(inputs, grid, padding_mode="border"):
     """F.grid_sample(inputs, grid, padding_mode=..., align_corners=False) through the fused kernel (no mip levels)."""
     return _MipmapWarp.apply(inputs, grid, 0.0, 0.0, _pad_code(padding_mode), 0)[0]
 
 
+def _default_ops():
+    from ..opset import cuda_ops
+    return cuda_ops()
+
+
 class Warp(nn.Module):
     """Spatial transform without anti-aliasing (reference antialiased_sampling.py:9-16)."""
 
+    def __init__(self, ops=None):
+        super().__init__()
+        self.ops = ops
+
     def forward(self, inputs, grid, padding_mode="border"):
-        return grid_sample_bilinear(inputs, grid, padding_mode)
+        ops = self.ops if self.ops is not None else _default_ops()
+        return ops.grid_sample(inputs, grid, padding_mode)
 
 
 class MipmapWarp(nn.Module):
     """Spatial transform with mipmap anti-aliasing (reference antialiased_sampling.py:19-60)."""
 
-    def __init__(self, max_num_levels=8):
+    def __init__(self, max_num_levels=8, ops=None):
         super().__init__()
+        self.ops = ops
         self.max_num_levels = max_num_levels
         f = torch.tensor([1.0, 3.0, 3.0, 1.0])
         f = f[:, None] * f[None, :]
@@ -129,14 +163,8 @@ class MipmapWarp(nn.Module):
         return self._levels / (self.max_num_levels - 1.0)
 
     def forward(self, inputs, grid, min_level=0.0, padding_mode="border"):
-        max_level = float(self.max_num_levels) - 1.0
-        wanted = int(math.ceil(max(max_level, float(min_level), 0.0)))
-        extra = feasible_levels(inputs.shape[2], inputs.shape[3], wanted)
-        if extra < wanted:  # tiny source: the reference only fails if such a level is actually selected
-            max_level = min(max_level, float(extra))
-            min_level = min(float(min_level), float(extra))
-        out, levels = _MipmapWarp.apply(inputs, grid, max_level, float(min_level), _pad_code(padding_mode), extra)
-        self._levels = levels if extra > 0 else torch.zeros(grid.shape[:3], device=grid.device)
+        ops = self.ops if self.ops is not None else _default_ops()
+        out, self._levels = ops.mipmap_warp(inputs, grid, self.max_num_levels, min_level, padding_mode)
         return out
 
     @staticmethod
@@ -152,8 +180,9 @@ class BilinearDownsample(nn.Module):
     """Reflect-pad + separable tent filter with stride (reference antialiased_sampling.py:241-256).
     Same buffers (`kernel_horz`, `kernel_vert`); SURVEY.md 8(f) rank 1 -- still two cuDNN depthwise convs here."""
 
-    def __init__(self, stride, channels):
+    def __init__(self, stride, channels, ops=None):
         super().__init__()
+        self.ops = ops
         self.stride = stride
         self.channels = channels
         ramp = np.arange(1, 2 * stride + 1, 2)
@@ -164,5 +193,5 @@ class BilinearDownsample(nn.Module):
         self.refl = nn.ReflectionPad2d(int(stride / 2))
 
     def forward(self, input):
-        rows = F.conv2d(self.refl(input), self.kernel_horz, stride=(1, self.stride), groups=self.channels)
-        return F.conv2d(rows, self.kernel_vert, stride=(self.stride, 1), groups=self.channels)
+        ops = self.ops if self.ops is not None else _default_ops()
+        return ops.bilinear_downsample(input, self.stride, self.kernel_horz, self.kernel_vert)

@@ -1,0 +1,129 @@
+"""One GANgealing training iteration (reference train.py:89-136) as a reusable object.
+
+Trainer.step() = gangealing_loss forward (G x2, STN, perceptual) -> TV / identity regularisers -> backward
+(DDP all-reduces the STN gradients over NCCL) -> Adam x2 -> EMA of the STN -> loss reduce.  It is what bench.py
+times for the "train images/sec at 256^2" metric.
+"""
+import dataclasses
+import math
+
+import torch
+from torch import nn, optim
+
+from ..stn import BilinearDownsample, get_stn
+from ..stylegan2 import Generator
+from . import distributed as gdist
+from .latent_learner import DirectionInterpolator
+from .losses import flow_identity_loss, gangealing_cluster_loss, gangealing_loss, total_variation_loss
+from .perceptual import get_perceptual_loss
+
+
+def requires_grad(model, flag=True):
+    for p in model.parameters():
+        p.requires_grad = flag
+
+
+def accumulate(model1, model2, decay=0.999):
+    """EMA of parameters (reference models/__init__.py:19-24), as two fused multi-tensor ops."""
+    p1 = dict(model1.named_parameters())
+    p2 = dict(model2.named_parameters())
+    keys = list(p1.keys())
+    a = [p1[k].data for k in keys]
+    b = [p2[k].data for k in keys]
+    torch._foreach_mul_(a, decay)
+    torch._foreach_add_(a, b, alpha=1 - decay)
+
+
+@dataclasses.dataclass
+class TrainConfig:
+    """Defaults = BASELINE config 2 (LSUN Cats 256^2, unimodal similarity+flow STN, fp32);
+    reference utils/base_argparse.py + scripts/training/lsun_cats_lpips.sh."""
+    gen_size: int = 256
+    flow_size: int = 128
+    dim_latent: int = 512
+    n_mlp: int = 8
+    gen_channel_multiplier: int = 2
+    stn_channel_multiplier: float = 0.5
+    transform: tuple = ("similarity", "flow")
+    num_heads: int = 1
+    flips: bool = False
+    ndirs: int = 1
+    inject: int = 5
+    batch: int = 5                    # per GPU (reference default)
+    padding_mode: str = "border"
+    sample_from_full_res: bool = False
+    tv_weight: float = 2500.0
+    flow_identity_weight: float = 0.0
+    stn_lr: float = 1e-3
+    ll_lr: float = 1e-2
+    freeze_ll: bool = False
+    psi: float = 0.5
+    seed: int = 0
+
+
+class Trainer:
+    """Builds G (frozen), STN (+EMA copy), latent learner, perceptual loss and optimisers; `step()` runs one iteration.
+    `ops`: None = the sm_100a op set; tests/bench's CPU legs pass the oracle's."""
+
+    def __init__(self, cfg, device, ops=None, distributed=False, seed_offset=0):
+        self.cfg, self.device, self.distributed = cfg, device, distributed
+        torch.manual_seed(cfg.seed)  # identical weights on every rank (stands in for the shared checkpoint)
+        self.generator = Generator(cfg.gen_size, cfg.dim_latent, cfg.n_mlp, channel_multiplier=cfg.gen_channel_multiplier,
+                                   ops=ops).to(device).eval()
+        kw = dict(flow_size=cfg.flow_size, supersize=cfg.gen_size if cfg.sample_from_full_res else cfg.flow_size,
+                  channel_multiplier=cfg.stn_channel_multiplier, num_heads=cfg.num_heads, ops=ops)
+        self.stn = get_stn(list(cfg.transform), **kw).to(device)
+        self.t_ema = get_stn(list(cfg.transform), **kw).to(device)
+        self.t_ema.load_state_dict(self.stn.state_dict())
+        self.ll = DirectionInterpolator(None, cfg.ndirs, cfg.inject, self.generator.n_latent, num_heads=cfg.num_heads,
+                                        dim_latent=cfg.dim_latent).to(device)
+        self.loss_fn = get_perceptual_loss(device, seed=cfg.seed + 1)
+        self.resize_fake2stn = (BilinearDownsample(cfg.gen_size // cfg.flow_size, 3, ops=ops).to(device)
+                                if cfg.gen_size > cfg.flow_size else nn.Sequential())
+        requires_grad(self.generator, False)
+        requires_grad(self.stn, True)
+        requires_grad(self.ll, True)
+        requires_grad(self.t_ema, False)
+        self.t_module, self.ll_module = self.stn, self.ll
+        if distributed:
+            ids = [torch.cuda.current_device()] if device != "cpu" and torch.device(device).type == "cuda" else None
+            self.stn = nn.parallel.DistributedDataParallel(self.stn, device_ids=ids, broadcast_buffers=False,
+                                                           gradient_as_bucket_view=True)
+            self.ll = nn.parallel.DistributedDataParallel(self.ll, device_ids=ids, broadcast_buffers=False)
+        fused = torch.device(device).type == "cuda"
+        self.t_optim = optim.Adam(self.t_module.parameters(), lr=cfg.stn_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused)
+        self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=cfg.ll_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused)
+        self.accum = 0.5 ** (32 / (10 * 1000))
+        self.zero = torch.tensor(0.0, device=device)
+        # each rank draws its own latents (reference train.py:193: seed*world + rank)
+        torch.manual_seed(cfg.seed * max(1, gdist.get_world_size()) + gdist.get_rank() + seed_offset)
+
+    def losses(self, z=None):
+        cfg = self.cfg
+        if cfg.num_heads > 1 or cfg.flips:
+            perceptual, delta_flow = gangealing_cluster_loss(
+                self.generator, self.stn, self.ll, self.loss_fn, self.resize_fake2stn, cfg.psi, cfg.batch, cfg.dim_latent,
+                cfg.freeze_ll, cfg.num_heads, cfg.flips, self.device, sample_from_full_res=cfg.sample_from_full_res,
+                padding_mode=cfg.padding_mode)
+        else:
+            perceptual, delta_flow = gangealing_loss(
+                self.generator, self.stn, self.ll, self.loss_fn, self.resize_fake2stn, cfg.psi, cfg.batch, cfg.dim_latent,
+                cfg.freeze_ll, self.device, sample_from_full_res=cfg.sample_from_full_res, z=z,
+                padding_mode=cfg.padding_mode)
+        tv = total_variation_loss(delta_flow) if cfg.tv_weight > 0 else self.zero
+        idt = flow_identity_loss(delta_flow) if cfg.flow_identity_weight > 0 else self.zero
+        return {"p": perceptual, "tv": tv, "f": idt}
+
+    def step(self, z=None):
+        """-> dict of (rank-0 averaged) scalar loss tensors, still on the device (no host sync here)."""
+        cfg = self.cfg
+        loss_dict = self.losses(z)
+        self.t_optim.zero_grad(set_to_none=True)
+        self.ll_optim.zero_grad(set_to_none=True)
+        full = loss_dict["p"] + cfg.tv_weight * loss_dict["tv"] + cfg.flow_identity_weight * loss_dict["f"]
+        full.backward()
+        self.t_optim.step()
+        if not cfg.freeze_ll:
+            self.ll_optim.step()
+        accumulate(self.t_ema, self.t_module, self.accum)
+        return gdist.reduce_loss_dict(loss_dict)

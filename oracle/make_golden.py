@@ -223,7 +223,45 @@ def gen_flow(ref_models):
     _save("flow_compose", **out)
 
 
-EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow]
+def gen_networks(ref_models):
+    """End-to-end fixtures: reference Generator / STN forward on CPU with construction-order-independent seeded
+    weights (oracle.opset.fill_parameters), explicit noise and fixed inputs."""
+    from oracle import opset
+    torch.Tensor.cuda = lambda self, *a, **k: self  # reference FlowHead.__init__ calls .cuda() (warping_heads.py:158)
+    from models.stylegan2.networks import Generator
+    from models.spatial_transformers.spatial_transformer import get_stn
+    out = {}
+    gen = torch.Generator().manual_seed(5000)
+    g = opset.fill_parameters(Generator(32, 32, 2, channel_multiplier=2).eval(), 1)
+    z = torch.randn(3, 32, generator=gen)
+    noise = [torch.randn(3, 1, n.shape[2], n.shape[3], generator=gen) for n in g.make_noise(1)]
+    with torch.no_grad():
+        img, lat = g([z], noise=noise, return_latents=True)
+    out["gen.z"], out["gen.image"], out["gen.latent"] = z, img, lat
+    for i, n in enumerate(noise):
+        out["gen.noise%d" % i] = n
+    for transforms in (["similarity"], ["similarity", "flow"]):
+        stn = get_stn(list(transforms), flow_size=64, supersize=128, channel_multiplier=0.5, num_heads=1).eval()
+        opset.fill_parameters(stn, 3, gain=0.3)
+        x = torch.randn(2, 3, 128, 128, generator=gen)
+        with torch.no_grad():
+            o, grid, fm = stn(x, return_warp=True, return_flow=True, padding_mode="reflection")
+        tag = "stn_" + "_".join(transforms)
+        out[tag + ".x"], out[tag + ".out"], out[tag + ".grid"], out[tag + ".fm"] = x, o, grid, fm
+    # BASELINE config 1 (SURVEY.md 8d): similarity-only STN @64 on CPU, non-identity head bias, 3 padding modes
+    stn = get_stn(["similarity"], flow_size=64, supersize=64, channel_multiplier=0.5, num_heads=1).eval()
+    opset.fill_parameters(stn, 5, gain=0.3)
+    x = torch.randn(4, 3, 64, 64, generator=gen)
+    with torch.no_grad():
+        stn.warp_head.linear.bias.copy_(torch.tensor([0.3, 0.2, 0.1, -0.1]))
+        for mode in ("border", "reflection", "zeros"):
+            o, grid, m = stn(x, return_warp=True, return_flow=True, padding_mode=mode)
+            out["cfg1.out." + mode] = o
+        out["cfg1.x"], out["cfg1.grid"], out["cfg1.M"] = x, grid, m
+    _save("networks", **out)
+
+
+EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks]
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,77 @@
+"""The CPU op namespace (test infrastructure): same entry names as gangealing_b200.opset.cuda_ops(), every
+entry a restatement from oracle/*.py.  tests/ and bench.py's CPU-baseline legs build the host-side networks
+with `ops=cpu_ops()` to run the reference algorithm end to end on the CPU; the product never does."""
+import types
+
+import torch
+import torch.nn.functional as F
+
+from . import flow as _flow
+from . import sampling as _smp
+from . import splat as _splat
+from . import stylegan2_ops as _so
+
+
+def _modulated_weight(weight, style, scale, demodulate=True, transposed=False, eps=1e-8):
+    w = _so.modulated_weight_ref(weight, style, scale, demodulate, eps)      # (B, O, I, k, k)
+    b, o, i, kh, kw = w.shape
+    if transposed:                                                            # networks.py:256-262
+        return w.transpose(1, 2).reshape(b * i, o, kh, kw)
+    return w.reshape(b * o, i, kh, kw)
+
+
+def _mipmap_warp(inputs, grid, max_num_levels=8, min_level=0.0, padding_mode="border"):
+    out, aux = _smp.mipmap_warp_ref(inputs, grid, max_num_levels, min_level, padding_mode, return_aux=True)
+    return out, aux["levels"]
+
+
+def _bilinear_downsample(x, stride, kernel_horz, kernel_vert):
+    return _smp.bilinear_downsample_ref(x, stride)
+
+
+def _flow_compose(low, mask, identity, base_warp=None, alpha=None, downsample=8):
+    return _flow.flow_compose_ref(low, mask, identity, base_warp, alpha, downsample)
+
+
+_ops = None
+
+
+def cpu_ops():
+    global _ops
+    if _ops is None:
+        _ops = types.SimpleNamespace(
+            name="cpu-oracle",
+            upfirdn2d=_so.upfirdn2d_ref,
+            fused_leaky_relu=_so.fused_leaky_relu_ref,
+            noise_bias_act=_so.noise_bias_act_ref,
+            blur_noise_bias_act=_so.blur_noise_bias_act_ref,
+            conv2d=F.conv2d,
+            conv_transpose2d=F.conv_transpose2d,
+            modulated_weight=_modulated_weight,
+            mipmap_warp=_mipmap_warp,
+            grid_sample=_smp.warp_ref,
+            bilinear_downsample=_bilinear_downsample,
+            flow_compose=_flow_compose,
+            splat2d=_splat.splat2d_ref,
+        )
+    return _ops
+
+
+def fill_parameters(module, seed=0, gain=1.0):
+    """Deterministic, construction-order-independent initialisation: every parameter/buffer is drawn from a
+    generator seeded by (seed, its qualified name).  Lets the golden script (reference modules) and the tests
+    (this repo's modules) hold bit-identical weights without shipping checkpoints."""
+    import zlib
+    with torch.no_grad():
+        for name, t in list(module.named_parameters()) + list(module.named_buffers()):
+            if not t.is_floating_point():
+                continue
+            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+            leaf = name.rsplit(".", 1)[-1]
+            if leaf in ("kernel", "blur_filter", "kernel_horz", "kernel_vert", "one_hot", "identity_flow"):
+                continue  # derived constants
+            vals = torch.randn(t.shape, generator=g) * gain
+            if leaf == "bias" or name.endswith("noise.weight"):
+                vals = vals * 0.1
+            t.copy_(vals.to(t.dtype))
+    return module
