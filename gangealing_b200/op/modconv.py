@@ -1,15 +1,42 @@
-"""Modulated-convolution weight path: modulate -> demodulate -> (transpose for the up-conv) in fused kernels.
+"""Modulated-convolution weight path: modulate -> demodulate -> (transposed layout for the up-conv), fused.
 
 reference: models/stylegan2/networks.py:233-253 (`weight = scale*W*style`, `demod = rsqrt(sum w^2 + 1e-8)`,
-`weight *= demod`, reshape / transpose for conv_transpose2d :255-262): ~6 ATen launches that materialise three
-(B, O, I, k, k) temporaries per layer.  `modulated_weight` is the op-level entry used by ModulatedConv2d.
+`weight *= demod`) and :255-262 (transpose + reshape for conv_transpose2d): ~6 ATen launches materialising three
+(B, O, I, k, k) temporaries per layer.  Here (csrc/modconv.cu):
+    demod[b,o] = rsqrt(scale^2 * sum_i Wsq[o,i] * style[b,i]^2 + eps)    one tcgen05 (tensor-core) GEMM
+    out        = scale * W * style[b,i] * demod[b,o]                     one pass, written in the conv's layout
+`Wsq = sum_k W^2` and the pre-transposed filter bank are cached per (storage, version) -- the generator is frozen.
+Backward (w.r.t. the style only -- the generator's filters never need a gradient in GANgealing):
+    T[b,o,i] = sum_k g[b,o,i,k] W[o,i,k];  gd = scale * sum_i T s;  gs = scale * sum_o T d - scale^2 s * ((gd d^3) @ Wsq)
 """
 import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _lib
+
+_cache = {}
+
+
+def _derived(weight3, need_t):
+    """(Wsq (O, I), W^T (I, O, kk) or None) for a filter bank, cached on (data_ptr, version, shape)."""
+    key = (weight3.data_ptr(), weight3._version, tuple(weight3.shape), weight3.device)
+    ent = _cache.get(key)
+    if ent is None:
+        if len(_cache) > 256:
+            _cache.clear()
+        o, i, kk = weight3.shape
+        wsq = torch.empty((o, i), dtype=torch.float32, device=weight3.device)
+        _lib.check(_lib.load().gg_modconv_wsq(wsq.data_ptr(), weight3.data_ptr(), o, i, kk, _lib.stream()), "gg_modconv_wsq")
+        ent = [wsq, None]
+        _cache[key] = ent
+    if need_t and ent[1] is None:
+        ent[1] = weight3.transpose(0, 1).contiguous()
+    return ent[0], ent[1]
 
 
 def modulated_weight_composite(weight, style, scale, demodulate=True, transposed=False, eps=1e-8):
-    """Plain tensor-op formulation (differentiable w.r.t. everything); used when the filter bank itself needs a
-    gradient (never the case for GANgealing's frozen generator) until the fused kernels take over that case too."""
+    """Plain tensor-op formulation, differentiable w.r.t. the filters too (not needed by GANgealing's frozen G)."""
     b = style.shape[0]
     _, o, i, kh, kw = weight.shape
     w = (scale * weight) * style.reshape(b, 1, i, 1, 1)
@@ -20,7 +47,59 @@ def modulated_weight_composite(weight, style, scale, demodulate=True, transposed
     return w.reshape(b * o, i, kh, kw)
 
 
+class _ModulatedWeight(Function):
+    @staticmethod
+    def forward(ctx, weight, style, scale, demodulate, transposed, eps):
+        _lib.require_cuda(weight, style)
+        _, o, i, kh, kw = weight.shape
+        kk = kh * kw
+        b = style.shape[0]
+        w3 = weight.detach().reshape(o, i, kk)
+        if w3.dtype != torch.float32 or not w3.is_contiguous():
+            w3 = w3.float().contiguous()
+        s = style.detach()
+        if s.dtype != torch.float32 or not s.is_contiguous():
+            s = s.float().contiguous()
+        lib = _lib.load()
+        st = _lib.stream()
+        wsq, wt = _derived(w3, transposed)
+        demod = None
+        if demodulate:
+            demod = torch.empty((b, o), dtype=torch.float32, device=s.device)
+            for b0 in range(0, b, 256):  # the tensor-core tile holds at most 256 batch columns
+                nb = min(256, b - b0)
+                rc = lib.gg_modconv_demod(demod[b0:].data_ptr(), wsq.data_ptr(), s[b0:].data_ptr(), scale, eps, nb, o, i, st)
+                _lib.check(rc, "gg_modconv_demod")
+        out = torch.empty((b * i, o, kh, kw) if transposed else (b * o, i, kh, kw), dtype=torch.float32, device=s.device)
+        rc = lib.gg_modconv_modulate(out.data_ptr(), (wt if transposed else w3).data_ptr(), s.data_ptr(), _lib.ptr(demod),
+                                     scale, b, o, i, kk, 1 if transposed else 0, st)
+        _lib.check(rc, "gg_modconv_modulate")
+        ctx.save_for_backward(w3, s, demod, wsq)
+        ctx.cfg = (scale, transposed, (o, i, kh, kw), style.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        w3, s, demod, wsq = ctx.saved_tensors
+        scale, transposed, (o, i, kh, kw), style_dtype = ctx.cfg
+        b = s.shape[0]
+        g = grad_out.reshape(b, i, o, kh * kw).transpose(1, 2) if transposed else grad_out.reshape(b, o, i, kh * kw)
+        t = torch.einsum("boik,oik->boi", g.float(), w3)
+        if demod is not None:
+            gd = scale * torch.einsum("boi,bi->bo", t, s)
+            gs = scale * torch.einsum("boi,bo->bi", t, demod) - (scale * scale) * s * ((gd * demod.pow(3)) @ wsq)
+        else:
+            gs = scale * t.sum(dim=1)
+        return None, gs.to(style_dtype), None, None, None, None
+
+
 def modulated_weight(weight, style, scale, demodulate=True, transposed=False, eps=1e-8):
     """weight (1, O, I, k, k), style (B, I) -> per-sample filters for the grouped convolution:
     (B*O, I, k, k), or (B*I, O, k, k) when `transposed` (the layout conv_transpose2d(groups=B) wants)."""
-    return modulated_weight_composite(weight, style, scale, demodulate, transposed, eps)
+    _, o, i, kh, kw = weight.shape
+    inner = (o if transposed else i) * kh * kw
+    if weight.requires_grad or inner % 4 != 0:
+        # filters that need a gradient (never in GANgealing) or odd tiny banks (to-RGB: O = 3, k = 1, I % 4 == 0 is fine)
+        return modulated_weight_composite(weight, style, scale, demodulate, transposed, eps)
+    return _ModulatedWeight.apply(weight, style, float(scale), bool(demodulate), bool(transposed), float(eps))

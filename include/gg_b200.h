@@ -193,6 +193,24 @@ GG_API int gg_splat2d_forward(float* out, void* workspace, const float* input, c
                               const float* values, const float* sigma, int64_t N, int64_t P, int C, int H,
                               int W, int soft_normalize, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Modulated-convolution weight path -- replaces the tensor-op chain of ModulatedConv2d.forward
+ *   reference: models/stylegan2/networks.py:233-253 (modulate, demodulate), :255-262 (layout for the up-conv)
+ *   weight (O, I, kk) fp32 [kk = k*k]; style (B, I) fp32 (output of the modulation EqualLinear).
+ *   gg_modconv_wsq      wsq[o,i] = sum_kk weight[o,i,kk]^2
+ *   gg_modconv_demod    demod[b,o] = rsqrt(scale^2 * sum_i wsq[o,i]*style[b,i]^2 + eps)   (B <= 256)
+ *                       tcgen05.mma kind::tf32 with a hi/lo operand split (fp32-grade accuracy), TMEM accumulator
+ *   gg_modconv_modulate out = scale * weight * style[b,i] * demod[b,o]   (demod == NULL: no demodulation)
+ *                       transposed == 0: out (B, O, I, kk), `weight` given as (O, I, kk)
+ *                       transposed != 0: out (B, I, O, kk), `weight` given PRE-TRANSPOSED as (I, O, kk)
+ *                       (I*kk, resp. O*kk, must be a multiple of 4)
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int gg_modconv_wsq(float* wsq, const float* weight, int O, int I, int kk, void* stream);
+GG_API int gg_modconv_demod(float* demod, const float* wsq, const float* style, float scale, float eps, int B,
+                            int O, int I, void* stream);
+GG_API int gg_modconv_modulate(float* out, const float* weight, const float* style, const float* demod,
+                               float scale, int B, int O, int I, int kk, int transposed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

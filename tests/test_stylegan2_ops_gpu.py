@@ -259,3 +259,29 @@ def test_blur_noise_bias_act(shape, pad):
         grads = torch.autograd.grad(y, leaves + ([] if rsg is None else [rsg]), go.to(DEV))
         for a, e, nm in zip(grads, grads_o, ("x", "noise", "noise_weight", "bias", "row_scale")):
             assert_close(a, e, rtol=3e-4, what="grad " + nm)
+
+
+# ------------------------------------------------------------------------------------------------ modulated weights
+@pytest.mark.parametrize("b,o,i,k,transposed,demod", [(5, 512, 512, 3, False, True), (3, 256, 512, 3, True, True),
+                                                      (2, 128, 128, 3, False, True), (4, 3, 512, 1, False, False),
+                                                      (32, 128, 256, 3, True, True), (2, 64, 32, 3, False, True),
+                                                      (300, 128, 64, 3, False, True)])
+def test_modulated_weight_tensor_core_demod(b, o, i, k, transposed, demod):
+    from gangealing_b200.op.modconv import modulated_weight
+    g = torch.Generator().manual_seed(b + o)
+    w = torch.randn(1, o, i, k, k, generator=g)
+    s = torch.randn(b, i, generator=g) + 1.0
+    scale = 1.0 / (i * k * k) ** 0.5
+    ref = so.modulated_weight_ref(w, s, scale, demod)
+    ref = ref.transpose(1, 2).reshape(b * i, o, k, k) if transposed else ref.reshape(b * o, i, k, k)
+    sg = s.to(DEV).requires_grad_(True)
+    out = modulated_weight(w.to(DEV), sg, scale, demod, transposed)
+    assert_close(out, ref, rtol=1e-4, what="modulated weight")   # hi/lo split TF32 GEMM: fp32-grade
+    # gradient w.r.t. the style vs autograd through the restatement
+    so_ = s.clone().requires_grad_(True)
+    r2 = so.modulated_weight_ref(w, so_, scale, demod)
+    r2 = r2.transpose(1, 2).reshape(b * i, o, k, k) if transposed else r2.reshape(b * o, i, k, k)
+    go = torch.randn(ref.shape, generator=g)
+    (gs_ref,) = torch.autograd.grad((r2 * go).sum(), so_)
+    (gs,) = torch.autograd.grad((out * go.to(DEV)).sum(), sg)
+    assert_close(gs, gs_ref, rtol=2e-3, what="style gradient")
