@@ -25,7 +25,9 @@ SIGNATURES = {
     "gg_last_error": (_c.c_char_p, []),
     "gg_sm_count": (_I, []),
     "gg_fused_bias_act": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _L, _L, _L, _P]),
-    "gg_noise_bias_act": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _L, _L, _L, _P]),
+    "gg_noise_bias_act": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _L, _L, _L, _P]),
+    "gg_channel_scale_workspace": (_L, [_L, _L]),
+    "gg_channel_scale": (_I, [_P, _P, _P, _P, _P, _P, _I, _L, _L, _P]),
     "gg_bias_act_backward_workspace": (_L, [_L, _L, _L]),
     "gg_bias_act_backward": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _L, _L, _L, _P]),
     "gg_upfirdn2d": (_I, [_P, _P, _P, _I, _L] + [_I] * 12 + [_P]),

@@ -74,11 +74,12 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 noise_bias_act_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ noise,
                       const float* __restrict__ noise_weight, const float* __restrict__ bias,
-                      float alpha, float scale, int64_t n_vec, int64_t C, int64_t HW) {
+                      const float* __restrict__ row_scale, float alpha, float scale, int64_t n_vec, int64_t C,
+                      int64_t HW) {
   const float nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
   const int64_t base = (static_cast<int64_t>(blockIdx.x) * kUnroll) * kThreads + threadIdx.x;
   Vec16<T> xv[kUnroll], nv[kUnroll];
-  float bv[kUnroll];
+  float bv[kUnroll], rv[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
     const int64_t v = base + static_cast<int64_t>(u) * kThreads;
@@ -90,6 +91,7 @@ noise_bias_act_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __r
       const int64_t n = row / C;
       const int64_t c = row - n * C;
       bv[u] = bias ? __ldg(bias + c) : 0.f;
+      rv[u] = row_scale ? __ldg(row_scale + row) : 1.f;
       if (noise) nv[u] = *reinterpret_cast<const Vec16<T>*>(noise + n * HW + p);  // re-read per channel: keep in L1/L2
     }
   }
@@ -100,9 +102,8 @@ noise_bias_act_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __r
       Vec16<T> o;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        float t = Cvt<T>::to_f(xv[u].v[k]);
-        if (noise) t = t + nw * Cvt<T>::to_f(nv[u].v[k]);
-        t += bv[u];
+        float t = fmaf(Cvt<T>::to_f(xv[u].v[k]), rv[u], bv[u]);
+        if (noise) t = fmaf(nw, Cvt<T>::to_f(nv[u].v[k]), t);
         o.v[k] = Cvt<T>::from_f((t > 0.f ? t : t * alpha) * scale);
       }
       st_vec_stream(out + v * VEC, o);
@@ -114,14 +115,14 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 noise_bias_act_scalar_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ noise,
                              const float* __restrict__ noise_weight, const float* __restrict__ bias,
-                             float alpha, float scale, int64_t numel, int64_t C, int64_t HW) {
+                             const float* __restrict__ row_scale, float alpha, float scale, int64_t numel, int64_t C,
+                             int64_t HW) {
   const float nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < numel;
        i += static_cast<int64_t>(gridDim.x) * kThreads) {
     const int64_t row = i / HW, p = i - row * HW, n = row / C, c = row - n * C;
-    float t = Cvt<T>::to_f(x[i]);
-    if (noise) t = t + nw * Cvt<T>::to_f(noise[n * HW + p]);
-    if (bias) t += __ldg(bias + c);
+    float t = Cvt<T>::to_f(x[i]) * (row_scale ? __ldg(row_scale + row) : 1.f) + (bias ? __ldg(bias + c) : 0.f);
+    if (noise) t = fmaf(nw, Cvt<T>::to_f(noise[n * HW + p]), t);
     out[i] = Cvt<T>::from_f((t > 0.f ? t : t * alpha) * scale);
   }
 }
@@ -231,6 +232,98 @@ __global__ void bias_grad_finish_kernel(float* __restrict__ grad_bias, const flo
   if (lane == 0) grad_bias[c] = acc;
 }
 
+// out[n,c,p] = x[n,c,p] * s[n*C + c]   (modulating the INPUT of a weight-shared convolution, networks.py:236/253
+// rewritten as conv(W, x*s)); with `y` given, also row_dot[row] = sum_p x[row,p]*y[row,p] (the gradient w.r.t. s).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+channel_scale_kernel(T* __restrict__ out, float* __restrict__ partial, const T* __restrict__ x, const T* __restrict__ y,
+                     const float* __restrict__ s, int64_t HW, int64_t chunk, int chunks_per_row) {
+  const int64_t row = blockIdx.x / chunks_per_row;
+  const int ck = blockIdx.x - row * chunks_per_row;
+  const int64_t p0 = static_cast<int64_t>(ck) * chunk;
+  const int64_t p1 = min(p0 + chunk, HW);
+  const int64_t off = row * HW;
+  const float sv = __ldg(s + row);
+  float acc = 0.f;
+  if constexpr (VEC > 1) {
+    const int64_t nv = (p1 - p0) / VEC;
+    for (int64_t v0 = 0; v0 < nv; v0 += static_cast<int64_t>(kThreads) * kUnroll) {
+      Vec16<T> xv[kUnroll], yv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t v = v0 + u * kThreads + threadIdx.x;
+        if (v < nv) {
+          xv[u] = ld_vec_stream(x + off + p0 + v * VEC);
+          if (y) yv[u] = ld_vec_stream(y + off + p0 + v * VEC);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t v = v0 + u * kThreads + threadIdx.x;
+        if (v < nv) {
+          Vec16<T> r;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float xf = Cvt<T>::to_f(xv[u].v[k]);
+            r.v[k] = Cvt<T>::from_f(xf * sv);
+            if (y) acc = fmaf(xf, Cvt<T>::to_f(yv[u].v[k]), acc);
+          }
+          st_vec_stream(out + off + p0 + v * VEC, r);
+        }
+      }
+    }
+  } else {
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += kThreads) {
+      const float xf = Cvt<T>::to_f(x[off + p]);
+      out[off + p] = Cvt<T>::from_f(xf * sv);
+      if (y) acc = fmaf(xf, Cvt<T>::to_f(y[off + p]), acc);
+    }
+  }
+  if (partial) {
+    __shared__ float wsum[kThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) t += wsum[w];
+      partial[blockIdx.x] = t;
+    }
+  }
+}
+
+// small rows (HW < 1024): one warp per row, 8 rows per CTA
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+channel_scale_rows_kernel(T* __restrict__ out, float* __restrict__ row_dot, const T* __restrict__ x,
+                          const T* __restrict__ y, const float* __restrict__ s, int64_t rows, int64_t HW) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t off = row * HW;
+  const float sv = __ldg(s + row);
+  float acc = 0.f;
+  for (int64_t p = lane; p < HW; p += 32) {
+    const float xf = Cvt<T>::to_f(x[off + p]);
+    out[off + p] = Cvt<T>::from_f(xf * sv);
+    if (y) acc = fmaf(xf, Cvt<T>::to_f(y[off + p]), acc);
+  }
+  if (row_dot) {
+    acc = warp_sum(acc);
+    if (lane == 0) row_dot[row] = acc;
+  }
+}
+
+// row_dot[row] = sum_k partial[row*K + k]
+__global__ void row_finish_kernel(float* __restrict__ row_dot, const float* __restrict__ partial, int64_t rows, int K) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += partial[r * K + k];
+  row_dot[r] = acc;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
@@ -267,7 +360,7 @@ int launch_flat(void* out, const void* x, const void* bias, const void* ref, int
 
 template <typename T>
 int launch_noise(void* out, const void* x, const void* noise, const float* nw, const float* bias,
-                 float alpha, float scale, int64_t N, int64_t C, int64_t HW, cudaStream_t st) {
+                 const float* row_scale, float alpha, float scale, int64_t N, int64_t C, int64_t HW, cudaStream_t st) {
   constexpr int V = 16 / sizeof(T);
   const int64_t numel = N * C * HW;
   const bool vec = (HW % V == 0) && aligned16(out) && aligned16(x) && (!noise || aligned16(noise));
@@ -277,13 +370,13 @@ int launch_noise(void* out, const void* x, const void* noise, const float* nw, c
     const int64_t grid = (n_vec + per_cta - 1) / per_cta;
     if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "noise_bias_act: tensor too large");
     noise_bias_act_kernel<T, V><<<static_cast<unsigned>(grid), kThreads, 0, st>>>(
-        static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(noise), nw, bias, alpha,
+        static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(noise), nw, bias, row_scale, alpha,
         scale, n_vec, C, HW);
   } else {
     int64_t grid = (numel + kThreads - 1) / kThreads;
     if (grid > 148 * 16) grid = 148 * 16;
     noise_bias_act_scalar_kernel<T><<<static_cast<unsigned>(grid), kThreads, 0, st>>>(
-        static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(noise), nw, bias, alpha,
+        static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(noise), nw, bias, row_scale, alpha,
         scale, numel, C, HW);
   }
   GG_CHECK_LAUNCH("noise_bias_act launch");
@@ -372,18 +465,74 @@ int gg_fused_bias_act(void* out, const void* x, const void* bias, const void* re
 }
 
 int gg_noise_bias_act(void* out, const void* x, const void* noise, const float* noise_weight,
-                      const float* bias, int dtype, float alpha, float scale, int64_t N, int64_t C,
-                      int64_t HW, void* stream) {
+                      const float* bias, const float* row_scale, int dtype, float alpha, float scale, int64_t N,
+                      int64_t C, int64_t HW, void* stream) {
   if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "noise_bias_act: negative size");
   if (N * C * HW == 0) return GG_OK;
   if (!out || !x) return fail(GG_ERR_BAD_ARG, "noise_bias_act: null tensor");
   auto st = static_cast<cudaStream_t>(stream);
   switch (dtype) {
-    case GG_F32: return launch_noise<float>(out, x, noise, noise_weight, bias, alpha, scale, N, C, HW, st);
-    case GG_F16: return launch_noise<__half>(out, x, noise, noise_weight, bias, alpha, scale, N, C, HW, st);
-    case GG_BF16: return launch_noise<__nv_bfloat16>(out, x, noise, noise_weight, bias, alpha, scale, N, C, HW, st);
+    case GG_F32: return launch_noise<float>(out, x, noise, noise_weight, bias, row_scale, alpha, scale, N, C, HW, st);
+    case GG_F16: return launch_noise<__half>(out, x, noise, noise_weight, bias, row_scale, alpha, scale, N, C, HW, st);
+    case GG_BF16: return launch_noise<__nv_bfloat16>(out, x, noise, noise_weight, bias, row_scale, alpha, scale, N, C, HW, st);
     default: return fail(GG_ERR_UNSUPPORTED, "noise_bias_act: dtype %d not supported", dtype);
   }
+}
+
+int64_t gg_channel_scale_workspace(int64_t rows, int64_t HW) {
+  if (rows <= 0 || HW <= 0) return 0;
+  const int64_t chunk = 16384;
+  return rows * ((HW + chunk - 1) / chunk) * static_cast<int64_t>(sizeof(float));
+}
+
+int gg_channel_scale(void* out, float* row_dot, void* workspace, const void* x, const void* y, const float* s, int dtype,
+                     int64_t rows, int64_t HW, void* stream) {
+  if (rows < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "channel_scale: negative size");
+  if (rows * HW == 0) return GG_OK;
+  if (!out || !x || !s) return fail(GG_ERR_BAD_ARG, "channel_scale: null tensor");
+  if (row_dot && (!y || !workspace)) return fail(GG_ERR_BAD_ARG, "channel_scale: row_dot needs y and a workspace");
+  const int64_t chunk = 16384;
+  const int K = static_cast<int>((HW + chunk - 1) / chunk);
+  const int64_t grid = rows * K;
+  if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "channel_scale: too many rows");
+  auto st = static_cast<cudaStream_t>(stream);
+  float* partial = row_dot ? static_cast<float*>(workspace) : nullptr;
+  const void* yy = row_dot ? y : nullptr;
+  if (HW < 1024) {
+    const unsigned g = static_cast<unsigned>((rows + (kThreads / 32) - 1) / (kThreads / 32));
+    switch (dtype) {
+      case GG_F32: channel_scale_rows_kernel<float><<<g, kThreads, 0, st>>>(static_cast<float*>(out), row_dot, static_cast<const float*>(x), static_cast<const float*>(yy), s, rows, HW); break;
+      case GG_F16: channel_scale_rows_kernel<__half><<<g, kThreads, 0, st>>>(static_cast<__half*>(out), row_dot, static_cast<const __half*>(x), static_cast<const __half*>(yy), s, rows, HW); break;
+      case GG_BF16: channel_scale_rows_kernel<__nv_bfloat16><<<g, kThreads, 0, st>>>(static_cast<__nv_bfloat16*>(out), row_dot, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(yy), s, rows, HW); break;
+      default: return fail(GG_ERR_UNSUPPORTED, "channel_scale: dtype %d not supported", dtype);
+    }
+    GG_CHECK_LAUNCH("channel_scale_rows launch");
+    return GG_OK;
+  }
+#define GG_CS(T_)                                                                                                   \
+  do {                                                                                                              \
+    constexpr int V = 16 / sizeof(T_);                                                                              \
+    const bool vec = (HW % V == 0) && aligned16(out) && aligned16(x) && (!yy || aligned16(yy));                     \
+    if (vec)                                                                                                        \
+      channel_scale_kernel<T_, V><<<static_cast<unsigned>(grid), kThreads, 0, st>>>(                                \
+          static_cast<T_*>(out), partial, static_cast<const T_*>(x), static_cast<const T_*>(yy), s, HW, chunk, K);  \
+    else                                                                                                            \
+      channel_scale_kernel<T_, 1><<<static_cast<unsigned>(grid), kThreads, 0, st>>>(                                \
+          static_cast<T_*>(out), partial, static_cast<const T_*>(x), static_cast<const T_*>(yy), s, HW, chunk, K);  \
+  } while (0)
+  switch (dtype) {
+    case GG_F32: GG_CS(float); break;
+    case GG_F16: GG_CS(__half); break;
+    case GG_BF16: GG_CS(__nv_bfloat16); break;
+    default: return fail(GG_ERR_UNSUPPORTED, "channel_scale: dtype %d not supported", dtype);
+  }
+#undef GG_CS
+  GG_CHECK_LAUNCH("channel_scale launch");
+  if (row_dot) {
+    row_finish_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, st>>>(row_dot, partial, rows, K);
+    GG_CHECK_LAUNCH("row_finish launch");
+  }
+  return GG_OK;
 }
 
 int64_t gg_bias_act_backward_workspace(int64_t N, int64_t C, int64_t HW) {

@@ -100,16 +100,21 @@ __device__ __forceinline__ void st_tile_chunk(float* tile, int r, int c, float4 
   *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(tile) + off) = v;
 }
 
+// NA = swizzle atoms (32-float k-blocks) staged per pipeline step: 2 when the B tiles are small enough, so that
+// 16 independent 16-byte loads per thread are in flight while the previous step's MMAs run.
+template <int NA>
 __global__ void __launch_bounds__(kDemodThreads)
 demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, const float* __restrict__ style,
                   float scale2, float eps, int B, int O, int I, int n_pad, int tmem_cols) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  // tiles: A_hi, A_lo (128 x 32 fp32 = 16 KB each), B_hi, B_lo (n_pad x 32 fp32)
+  // per atom: A_hi, A_lo (128 x 32 fp32 = 16 KB each), B_hi, B_lo (n_pad x 32 fp32 each)
   unsigned char* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // SWIZZLE_128B tiles: 1024-byte aligned
-  float* a_hi = reinterpret_cast<float*>(base);
-  float* a_lo = a_hi + 128 * kBlockK;
-  float* b_hi = a_lo + 128 * kBlockK;
-  float* b_lo = b_hi + n_pad * kBlockK;
+  const int a_elems = 128 * kBlockK, b_elems = n_pad * kBlockK;
+  float* tiles = reinterpret_cast<float*>(base);
+  auto a_hi = [&](int a) { return tiles + a * (2 * a_elems + 2 * b_elems); };
+  auto a_lo = [&](int a) { return a_hi(a) + a_elems; };
+  auto b_hi = [&](int a) { return a_lo(a) + a_elems; };
+  auto b_lo = [&](int a) { return b_hi(a) + b_elems; };
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ int failed;
@@ -134,40 +139,61 @@ demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, cons
   const uint32_t tmem_d = tmem_base_smem;
 
   const uint32_t idesc = make_idesc_tf32(128, n_pad);
+  const bool vec_ok = (I % 4 == 0) && ((reinterpret_cast<uintptr_t>(wsq) & 15) == 0);
+  const int o_row = o0 + tid;
+  const float* a_row = wsq + static_cast<int64_t>(min(o_row, O - 1)) * I;
+
+  // register staging of this thread's A row: NA atoms x 8 chunks of 4 floats
+  float4 ra[NA][8];
+  auto load_a = [&](int kb0) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int i = (kb0 + a) * kBlockK + c * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o_row < O) {
+          if (vec_ok && i + 3 < I) {
+            v = __ldg(reinterpret_cast<const float4*>(a_row + i));
+          } else {
+            if (i + 0 < I) v.x = __ldg(a_row + i + 0);
+            if (i + 1 < I) v.y = __ldg(a_row + i + 1);
+            if (i + 2 < I) v.z = __ldg(a_row + i + 2);
+            if (i + 3 < I) v.w = __ldg(a_row + i + 3);
+          }
+        }
+        ra[a][c] = v;
+      }
+  };
+
   uint32_t parity = 0;
   bool ok = true;
   const int k_blocks = (I + kBlockK - 1) / kBlockK;
-  for (int kb = 0; kb < k_blocks && ok; ++kb) {
-    const int i0 = kb * kBlockK;
-    // ---- stage A: row = tid (128 rows), 8 chunks of 4 floats
-    {
-      const int o = o0 + tid;
+  load_a(0);
+  for (int kb = 0; kb < k_blocks && ok; kb += NA) {
+    // ---- registers -> swizzled tiles (A), global -> tiles (B: squared styles, small)
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float v[4], hi[4], lo[4];
+        const float v[4] = {ra[a][c].x, ra[a][c].y, ra[a][c].z, ra[a][c].w};
+        float hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = i0 + c * 4 + j;
-          v[j] = (o < O && i < I) ? __ldg(wsq + static_cast<int64_t>(o) * I + i) : 0.f;
-          split_tf32(v[j], hi[j], lo[j]);
-        }
-        st_tile_chunk(a_hi, tid, c, make_float4(hi[0], hi[1], hi[2], hi[3]));
-        st_tile_chunk(a_lo, tid, c, make_float4(lo[0], lo[1], lo[2], lo[3]));
+        for (int j = 0; j < 4; ++j) split_tf32(v[j], hi[j], lo[j]);
+        st_tile_chunk(a_hi(a), tid, c, make_float4(hi[0], hi[1], hi[2], hi[3]));
+        st_tile_chunk(a_lo(a), tid, c, make_float4(lo[0], lo[1], lo[2], lo[3]));
       }
-    }
-    // ---- stage B: rows = batch entries (squared styles), n_pad rows
-    for (int r = tid; r < n_pad; r += kDemodThreads) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int rc = tid; rc < n_pad * 8; rc += kDemodThreads) {   // (row, chunk) pairs: coalesced over chunks
+        const int r = rc >> 3, c = rc & 7;
         float hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int i = i0 + c * 4 + j;
-          float s = (r < B && i < I) ? __ldg(style + static_cast<int64_t>(r) * I + i) : 0.f;
-          split_tf32(s * s, hi[j], lo[j]);
+          const int i = (kb + a) * kBlockK + c * 4 + j;
+          const float sv = (r < B && i < I) ? __ldg(style + static_cast<int64_t>(r) * I + i) : 0.f;
+          split_tf32(sv * sv, hi[j], lo[j]);
         }
-        st_tile_chunk(b_hi, r, c, make_float4(hi[0], hi[1], hi[2], hi[3]));
-        st_tile_chunk(b_lo, r, c, make_float4(lo[0], lo[1], lo[2], lo[3]));
+        st_tile_chunk(b_hi(a), r, c, make_float4(hi[0], hi[1], hi[2], hi[3]));
+        st_tile_chunk(b_lo(a), r, c, make_float4(lo[0], lo[1], lo[2], lo[3]));
       }
     }
     // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -175,20 +201,26 @@ demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, cons
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint64_t dah = make_smem_desc(smem_u32(a_hi)), dal = make_smem_desc(smem_u32(a_lo));
-      const uint64_t dbh = make_smem_desc(smem_u32(b_hi)), dbl = make_smem_desc(smem_u32(b_lo));
 #pragma unroll
-      for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-        const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 4) >> 4);   // +32 B per k-step inside the atom
-        umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, (kb | k) ? 1u : 0u);
-        umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-        umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+      for (int a = 0; a < NA; ++a) {
+        if (kb + a < k_blocks) {
+          const uint64_t dah = make_smem_desc(smem_u32(a_hi(a))), dal = make_smem_desc(smem_u32(a_lo(a)));
+          const uint64_t dbh = make_smem_desc(smem_u32(b_hi(a))), dbl = make_smem_desc(smem_u32(b_lo(a)));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 4) >> 4);   // +32 B per k-step inside the atom
+            umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, (kb | a | k) ? 1u : 0u);
+            umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+            umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+          }
+        }
       }
       // completion of all MMAs issued so far -> mbarrier (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
                    : "memory");
     }
-    ok = mbar_wait_bounded(&mma_bar, parity);   // tiles may be overwritten / accumulator read after this
+    if (kb + NA < k_blocks) load_a(kb + NA);   // next step's loads fly while the tensor core works
+    ok = mbar_wait_bounded(&mma_bar, parity);  // tiles may be overwritten / accumulator read after this
     parity ^= 1u;
   }
   if (!ok) failed = 1;
@@ -283,15 +315,23 @@ int gg_modconv_demod(float* demod, const float* wsq, const float* style, float s
   const int n_pad = (B + 15) / 16 * 16;
   int tmem_cols = 32;
   while (tmem_cols < n_pad) tmem_cols <<= 1;
-  const size_t smem = static_cast<size_t>(2 * 128 + 2 * n_pad) * kBlockK * sizeof(float) + 1024;
+  const int na = (n_pad <= 64 && I > kBlockK) ? 2 : 1;
+  const size_t smem = static_cast<size_t>(na) * (2 * 128 + 2 * n_pad) * kBlockK * sizeof(float) + 1024;
   static thread_local bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(demod_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(demod_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(demod_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "modconv_demod smem opt-in");
     configured = true;
   }
-  demod_umma_kernel<<<(O + 127) / 128, kDemodThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      demod, wsq, style, scale * scale, eps, B, O, I, n_pad, tmem_cols);
+  auto st = static_cast<cudaStream_t>(stream);
+  if (na == 2)
+    demod_umma_kernel<2><<<(O + 127) / 128, kDemodThreads, smem, st>>>(demod, wsq, style, scale * scale, eps, B, O, I,
+                                                                      n_pad, tmem_cols);
+  else
+    demod_umma_kernel<1><<<(O + 127) / 128, kDemodThreads, smem, st>>>(demod, wsq, style, scale * scale, eps, B, O, I,
+                                                                      n_pad, tmem_cols);
   GG_CHECK_LAUNCH("demod_umma launch");
   return GG_OK;
 }

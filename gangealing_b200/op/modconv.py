@@ -18,6 +18,136 @@ from .. import _lib
 _cache = {}
 
 
+def channel_scale_raw(x, s, y=None):
+    """out = x * s[n, c]; with `y`: also row_dot[n, c] = sum_hw x*y (fp32).  x: (N, C, H, W); s: (N, C) fp32."""
+    _lib.require_cuda(x, s, y)
+    x = x.contiguous()
+    n, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(n * c, 1)
+    s = s.reshape(n * c)
+    if s.dtype != torch.float32 or not s.is_contiguous():
+        s = s.float().contiguous()
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    dot = ws = None
+    if y is not None:
+        y = y.contiguous()
+        dot = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        ws = torch.empty(max(1, lib.gg_channel_scale_workspace(n * c, hw) // 4), dtype=torch.float32, device=x.device)
+    rc = lib.gg_channel_scale(out.data_ptr(), _lib.ptr(dot), _lib.ptr(ws), x.data_ptr(), _lib.ptr(y), s.data_ptr(),
+                              _lib.dtype_code(x), n * c, hw, _lib.stream())
+    _lib.check(rc, "gg_channel_scale")
+    return out, dot
+
+
+class _ChannelScale(Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        out, _ = channel_scale_raw(x, s.detach())
+        ctx.save_for_backward(x, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        need_x, need_s = ctx.needs_input_grad
+        if need_s:   # one pass: g*s and sum_hw g*x
+            gx, gs = channel_scale_raw(g, s.detach(), y=x)
+            return (gx if need_x else None), gs.reshape(s.shape).to(s.dtype)
+        return _ChannelScale.apply(g, s.detach()), None
+
+
+def channel_scale(x, s):
+    """x (N, C, H, W) * s (N, C)[:, :, None, None] in one fused pass (differentiable in both)."""
+    return _ChannelScale.apply(x, s)
+
+
+class _Demod(Function):
+    """demod[b, o] = rsqrt(scale^2 * sum_i Wsq[o, i] style[b, i]^2 + eps) on the tensor cores (tcgen05, TF32 hi/lo)."""
+
+    @staticmethod
+    def forward(ctx, weight, style, scale, eps):
+        _, o, i, kh, kw = weight.shape
+        w3 = weight.detach().reshape(o, i, kh * kw)
+        if w3.dtype != torch.float32 or not w3.is_contiguous():
+            w3 = w3.float().contiguous()
+        s = style.detach()
+        if s.dtype != torch.float32 or not s.is_contiguous():
+            s = s.float().contiguous()
+        wsq, _ = _derived(w3, False)
+        b = s.shape[0]
+        lib = _lib.load()
+        demod = torch.empty((b, o), dtype=torch.float32, device=s.device)
+        for b0 in range(0, b, 256):
+            nb = min(256, b - b0)
+            rc = lib.gg_modconv_demod(demod[b0:].data_ptr(), wsq.data_ptr(), s[b0:].data_ptr(), scale, eps, nb, o, i,
+                                      _lib.stream())
+            _lib.check(rc, "gg_modconv_demod")
+        ctx.save_for_backward(s, demod, wsq)
+        ctx.cfg = (scale, style.dtype)
+        return demod
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gd):
+        s, demod, wsq = ctx.saved_tensors
+        scale, style_dtype = ctx.cfg
+        gs = -(scale * scale) * s * ((gd.float() * demod.pow(3)) @ wsq)
+        return None, gs.to(style_dtype), None, None
+
+
+def demod_coefficients(weight, style, scale, eps=1e-8):
+    """(B, O) demodulation coefficients of ModulatedConv2d (reference networks.py:245-246), differentiable in `style`."""
+    if weight.requires_grad:
+        w = (scale * weight) * style.reshape(style.shape[0], 1, -1, 1, 1)
+        return torch.rsqrt(w.pow(2).sum([2, 3, 4]) + eps)
+    _lib.require_cuda(weight, style)
+    return _Demod.apply(weight, style, float(scale), float(eps))
+
+
+_wcache = {}
+
+
+def shared_conv_weight(weight, scale, transposed):
+    """scale * W as the weight of a weight-SHARED convolution: (O, I, k, k), or (I, O, k, k) for conv_transpose2d.
+    Cached per (storage, version) for frozen filter banks."""
+    if weight.requires_grad:
+        w = weight[0] * scale
+        return w.transpose(0, 1) if transposed else w
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device, float(scale), bool(transposed), weight.dtype)
+    w = _wcache.get(key)
+    if w is None:
+        if len(_wcache) > 256:
+            _wcache.clear()
+        w = (weight.detach()[0] * scale)
+        w = w.transpose(0, 1).contiguous() if transposed else w.contiguous()
+        _wcache[key] = w
+    return w
+
+
+def modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, padding=1, eps=1e-8):
+    """ModulatedConv2d's convolution, B200-first: conv(scale*W*s, x) == conv(scale*W, x*s), so ONE weight-shared
+    (dense, tensor-core friendly) cuDNN convolution replaces the reference's grouped convolution over B materialised
+    filter banks (networks.py:255-280); measured 1.3-3x faster on B200 (tools/convbench.py).
+    Returns (raw, demod): the caller applies `demod` (B, O) -- or None -- as the per-(sample, channel) row scale of its
+    fused activation tail (it commutes with the blur)."""
+    from . import conv2d_gradfix
+    _, o, i, kh, kw = weight.shape
+    if kh == 1 and kw == 1 and not upsample and not demodulate:
+        # to-RGB: a (3 x C) matrix per sample -- one batched GEMM reads the activation once, nothing is re-written
+        wm = (scale * weight[0, :, :, 0, 0]).unsqueeze(0) * style.unsqueeze(1)            # (B, O, I)
+        b, _, h, w_ = x.shape
+        return torch.bmm(wm.type(x.dtype), x.reshape(b, i, h * w_)).reshape(b, o, h, w_), None
+    xs = channel_scale(x, style)
+    w = shared_conv_weight(weight, scale, transposed=upsample)
+    if upsample:
+        raw = conv2d_gradfix.conv_transpose2d(xs, w.type(x.dtype), padding=0, stride=2)
+    else:
+        raw = conv2d_gradfix.conv2d(xs, w.type(x.dtype), padding=padding)
+    d = demod_coefficients(weight, style, scale, eps) if demodulate else None
+    return raw, d
+
+
 def _derived(weight3, need_t):
     """(Wsq (O, I), W^T (I, O, kk) or None) for a filter bank, cached on (data_ptr, version, shape)."""
     key = (weight3.data_ptr(), weight3._version, tuple(weight3.shape), weight3.device)

@@ -11,6 +11,7 @@ from torch.autograd import Function
 
 from .. import _lib
 from .fused_act import bias_act_backward_raw
+from .modconv import channel_scale_raw
 from .upfirdn2d import UpFirDn2d, _taps, grad_pad
 
 
@@ -47,12 +48,10 @@ class _StyledTail(Function):
         b = _f32(bias.reshape(-1)) if bias is not None else None
         rs = _f32(row_scale.reshape(-1)) if row_scale is not None else None
         if kernel is None:
-            if rs is not None:
-                raise RuntimeError("noise_bias_act: row_scale is only supported on the blur path")
             out = torch.empty_like(x)
             nz = _noise_plane(noise, x, in_h, in_w)
             rc = lib.gg_noise_bias_act(out.data_ptr(), x.data_ptr(), _lib.ptr(nz), _lib.ptr(nw), _lib.ptr(b),
-                                       _lib.dtype_code(x), negative_slope, scale, n, c, in_h * in_w,
+                                       _lib.ptr(rs), _lib.dtype_code(x), negative_slope, scale, n, c, in_h * in_w,
                                        _lib.stream())
             _lib.check(rc, "gg_noise_bias_act")
         else:
@@ -101,27 +100,29 @@ class _StyledTail(Function):
                     g_noise = g_noise.sum_to_size(noise.shape)
         if need_x or need_rs:
             if kernel is None:
-                g_x = gx
+                g_t = gx
             else:
                 kh, kw = kernel.shape
                 gp = grad_pad(in_size[2], in_size[3], out.shape[2], out.shape[3], kh, kw, (1, 1), (1, 1), pad)
                 g_t = UpFirDn2d.apply(gx, torch.flip(kernel, [0, 1]), (1, 1), (1, 1), gp)  # adjoint blur
-                if row_scale is not None:
-                    rs = row_scale.reshape(in_size[0], in_size[1], 1, 1).to(g_t.dtype)
-                    if need_rs:
-                        g_rs = (g_t * x_saved).sum(dim=(2, 3)).reshape(row_scale.shape).to(row_scale.dtype)
-                    g_x = g_t * rs
-                else:
-                    g_x = g_t
+            if row_scale is not None:
+                # one fused pass: g_x = g_t * rs  and  g_rs = sum_hw g_t * x   (<B(x), g> = <x, B^T g>)
+                g_x, dot = channel_scale_raw(g_t, row_scale.detach().reshape(in_size[0], in_size[1]),
+                                             y=x_saved if need_rs else None)
+                if need_rs:
+                    g_rs = dot.reshape(row_scale.shape).to(row_scale.dtype)
+            else:
+                g_x = g_t
         if gbias is not None:
             gbias = gbias.to(out.dtype)
         return (g_x if need_x else None), g_noise, g_nw, gbias, None, None, g_rs, None, None
 
 
-def noise_bias_act(x, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5):
-    """leaky_relu(x + noise_weight*noise + bias[c]) * scale in one pass.
-    x: (N, C, H, W); noise: (N, 1, H, W) (or broadcastable) or None; noise_weight: 1-element tensor; bias: (C,)."""
-    return _StyledTail.apply(x, noise, noise_weight, bias, None, None, None, negative_slope, scale)
+def noise_bias_act(x, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5, row_scale=None):
+    """leaky_relu(row_scale*x + noise_weight*noise + bias[c]) * scale in one pass.
+    x: (N, C, H, W); noise: (N, 1, H, W) (or broadcastable) or None; noise_weight: 1-element tensor; bias: (C,);
+    row_scale: (N, C) or None (demodulation coefficients of a weight-shared modulated convolution)."""
+    return _StyledTail.apply(x, noise, noise_weight, bias, None, None, row_scale, negative_slope, scale)
 
 
 def blur_noise_bias_act(x, kernel, pad, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5,

@@ -27,6 +27,8 @@ def cuda_ops():
             conv2d=_op.conv2d_gradfix.conv2d,
             conv_transpose2d=_op.conv2d_gradfix.conv_transpose2d,
             modulated_weight=_mod.modulated_weight,
+            modulated_conv2d=_mod.modulated_conv2d,
+            channel_scale=_mod.channel_scale,
             mipmap_warp=_smp.mipmap_warp,
             grid_sample=_smp.grid_sample_bilinear,
             bilinear_downsample=_smp.bilinear_downsample,

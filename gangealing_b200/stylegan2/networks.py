@@ -156,13 +156,32 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def forward(self, input, style, fuse_blur=True):
-        batch, in_channel, height, width = input.shape
+    def conv_raw(self, input, style):
+        """-> (raw, demod): the convolution WITHOUT blur and demodulation, plus the (B, O) demodulation coefficients
+        (or None when they are already folded into the result).  The op set chooses the formulation: the sm_100a set
+        runs ONE weight-shared convolution on modulated activations, the CPU oracle the reference's grouped one."""
         style = self.modulation(style)
+        plain = not (self.normalize or (input.dtype == torch.float16 and self.demodulate)) and not self.downsample
+        if plain:
+            return self.ops.modulated_conv2d(input, self.weight, style, self.scale, self.demodulate, self.upsample,
+                                             self.padding, self.eps)
+        return self._reference_formulation(input, style), None
+
+    def forward(self, input, style, fuse_blur=True):
+        raw, demod = self.conv_raw(input, style)
+        if demod is not None:
+            raw = self.ops.channel_scale(raw, demod)
+        if self.upsample and fuse_blur:
+            return self.blur(raw)
+        return raw
+
+    def _reference_formulation(self, input, style):
+        """Per-sample filter banks + grouped convolution (reference networks.py:236-280): kept for the fp16
+        pre-scaling branch and the (unused) downsampling variant."""
+        batch, in_channel, height, width = input.shape
         weight = self.weight
         scale = self.scale
         if self.normalize or (input.dtype == torch.float16 and self.demodulate):
-            # fp16 range pre-scaling of the reference (networks.py:237-242); dead on the default run_fp32 path
             style = style / torch.max(torch.abs(style))
             fan = torch.tensor(in_channel * weight.size(3) * weight.size(4), dtype=torch.float32)
             weight = scale * weight * torch.sqrt(1.0 / fan) / torch.amax(torch.abs(scale * weight), dim=(2, 3, 4), keepdims=True)
@@ -172,9 +191,7 @@ class ModulatedConv2d(nn.Module):
         x = input.reshape(1, batch * in_channel, height, width)
         if self.upsample:
             out = self.ops.conv_transpose2d(x, w, padding=0, stride=2, groups=batch)
-            out = out.view(batch, self.out_channel, out.shape[2], out.shape[3])
-            return self.blur(out) if fuse_blur else out
-        if self.downsample:
+        elif self.downsample:
             xb = self.blur(input)
             out = self.ops.conv2d(xb.reshape(1, batch * in_channel, xb.shape[2], xb.shape[3]), w, padding=0, stride=2,
                                   groups=batch)
@@ -223,7 +240,7 @@ class StyledConv(nn.Module):
 
     def forward(self, input, style, noise=None):
         act = self.activate
-        raw = self.conv(input, style, fuse_blur=False)
+        raw, demod = self.conv.conv_raw(input, style)
         if self.conv.upsample:
             blur = self.conv.blur
             out_h = raw.shape[2] + blur.pad[0] + blur.pad[1] - blur.kernel.shape[0] + 1
@@ -231,10 +248,11 @@ class StyledConv(nn.Module):
             if noise is None:
                 noise = NoiseInjection.sample(raw.shape[0], out_h, out_w, raw)
             return self.ops.blur_noise_bias_act(raw, blur.kernel, blur.pad, noise, self.noise.weight, act.bias,
-                                                act.negative_slope, act.scale)
+                                                act.negative_slope, act.scale, row_scale=demod)
         if noise is None:
             noise = NoiseInjection.sample(raw.shape[0], raw.shape[2], raw.shape[3], raw)
-        return self.ops.noise_bias_act(raw, noise, self.noise.weight, act.bias, act.negative_slope, act.scale)
+        return self.ops.noise_bias_act(raw, noise, self.noise.weight, act.bias, act.negative_slope, act.scale,
+                                       row_scale=demod)
 
 
 class ToRGB(nn.Module):

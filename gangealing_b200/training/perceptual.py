@@ -54,8 +54,11 @@ class PerceptualLoss(nn.Module):
         return feat / (torch.sqrt(torch.sum(feat ** 2, dim=1, keepdim=True)) + eps)
 
     def forward(self, in0, in1):
-        f0 = self.net((in0 - self.shift) / self.scale)
-        f1 = self.net((in1 - self.shift) / self.scale)
+        # channels_last: cuDNN's tensor-core kernels are NHWC-native; NCHW inputs cost a layout conversion around
+        # every convolution (22% of the step in profiles/r01_step_launches_b8_summary.txt)
+        cl = torch.channels_last if in0.is_cuda else torch.contiguous_format
+        f0 = self.net(((in0 - self.shift) / self.scale).contiguous(memory_format=cl))
+        f1 = self.net(((in1 - self.shift) / self.scale).contiguous(memory_format=cl))
         val = 0
         for a, b in zip(f0, f1):
             val = val + ((self._unit(a) - self._unit(b)) ** 2).sum(dim=1, keepdim=True).mean([2, 3], keepdim=True)
@@ -67,4 +70,7 @@ def get_perceptual_loss(device, seed=0):
     torch.manual_seed(seed)
     loss = PerceptualLoss()
     torch.random.set_rng_state(g)
-    return loss.to(device)
+    loss = loss.to(device)
+    if torch.device(device).type == "cuda":
+        loss = loss.to(memory_format=torch.channels_last)
+    return loss

@@ -91,8 +91,12 @@ class Trainer:
                                                            gradient_as_bucket_view=True)
             self.ll = nn.parallel.DistributedDataParallel(self.ll, device_ids=ids, broadcast_buffers=False)
         fused = torch.device(device).type == "cuda"
-        self.t_optim = optim.Adam(self.t_module.parameters(), lr=cfg.stn_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused)
-        self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=cfg.ll_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused)
+        # capturable: the optimiser state lives on the device so a whole iteration can be replayed as a CUDA graph
+        self.t_optim = optim.Adam(self.t_module.parameters(), lr=cfg.stn_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused,
+                                  capturable=fused)
+        self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=cfg.ll_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused,
+                                   capturable=fused)
+        self._graph = None
         self.accum = 0.5 ** (32 / (10 * 1000))
         self.zero = torch.tensor(0.0, device=device)
         # each rank draws its own latents (reference train.py:193: seed*world + rank)
@@ -115,7 +119,43 @@ class Trainer:
         return {"p": perceptual, "tv": tv, "f": idt}
 
     def step(self, z=None):
-        """-> dict of (rank-0 averaged) scalar loss tensors, still on the device (no host sync here)."""
+        """-> dict of (rank-0 averaged) scalar loss tensors, still on the device (no host sync here).
+        After `capture()` the iteration is replayed from a CUDA graph (z, if given, is copied into its static input)."""
+        if self._graph is not None:
+            if z is None:
+                self._static_z.normal_()
+            else:
+                self._static_z.copy_(z, non_blocking=True)
+            self._graph.replay()
+            return self._static_out
+        return self._eager_step(z)
+
+    def capture(self, warmup=3):
+        """Capture one whole iteration (G x2, STN, loss, backward, Adam x2, EMA) into a CUDA graph.
+
+        The reference's loop is launch-bound at its recipe's per-GPU batch (thousands of launches per step,
+        SURVEY.md 8e "scaling risk"); every op on this path is graph-safe: static shapes, no host sync (the fused
+        sampler drops MipmapWarp's `.item()`), device-side RNG and optimiser state.  Single-process only."""
+        if self.distributed:
+            raise RuntimeError("capture() is for single-process runs; DDP steps run eagerly")
+        cfg = self.cfg
+        self._static_z = torch.randn(cfg.batch, cfg.dim_latent, device=self.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step(self._static_z)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        self.t_optim.zero_grad(set_to_none=True)
+        self.ll_optim.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            out = self._eager_step(self._static_z)
+            self._static_out = {k: v.detach() for k, v in out.items()}
+        self._graph = graph
+        return self
+
+    def _eager_step(self, z=None):
         cfg = self.cfg
         loss_dict = self.losses(z)
         self.t_optim.zero_grad(set_to_none=True)

@@ -65,13 +65,26 @@ GG_API int gg_fused_bias_act(void* out, const void* x, const void* bias, const v
 /* ------------------------------------------------------------------------------------------------
  * gg_noise_bias_act -- NoiseInjection + FusedLeakyReLU of a StyledConv in one pass
  *   reference: models/stylegan2/networks.py:291-298 (noise) + :344-350 + op/fused_act.py:52-58
- *   out[n,c,p] = lrelu(x[n,c,p] + noise_weight[0]*noise[n,p] + bias[c], alpha) * scale
+ *   out[n,c,p] = lrelu(row_scale[n*C+c]*x[n,c,p] + noise_weight[0]*noise[n,p] + bias[c], alpha) * scale
  *   x/out: (N, C, HW) `dtype`;  noise: (N, HW) `dtype` or NULL;  noise_weight: 1 fp32 (device) or
- *   NULL (=1);  bias: C fp32 or NULL.
+ *   NULL (=1);  bias: C fp32 or NULL;  row_scale: N*C fp32 or NULL (=1; the demodulation coefficients when
+ *   the convolution ran with shared weights on modulated activations).
  * ---------------------------------------------------------------------------------------------- */
 GG_API int gg_noise_bias_act(void* out, const void* x, const void* noise, const float* noise_weight,
-                             const float* bias, int dtype, float alpha, float scale, int64_t N,
-                             int64_t C, int64_t HW, void* stream);
+                             const float* bias, const float* row_scale, int dtype, float alpha, float scale,
+                             int64_t N, int64_t C, int64_t HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * gg_channel_scale -- per-(sample, channel) scaling of an activation, the modulation of
+ *   reference models/stylegan2/networks.py:236,243 applied to the convolution's INPUT instead of its weights:
+ *   conv(scale*W*s[b,i], x) == conv(scale*W, x*s[b,i])  -> weight-shared (dense, tensor-core friendly) convolutions.
+ *   out[r,p] = x[r,p] * s[r]        rows r = n*C + c, p < HW
+ *   row_dot[r] = sum_p x[r,p]*y[r,p]   (optional; with y = upstream gradient this is d/ds; fp32, deterministic;
+ *   needs gg_channel_scale_workspace(rows, HW) bytes)
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int64_t gg_channel_scale_workspace(int64_t rows, int64_t HW);
+GG_API int gg_channel_scale(void* out, float* row_dot, void* workspace, const void* x, const void* y,
+                            const float* s, int dtype, int64_t rows, int64_t HW, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * gg_bias_act_backward -- FusedLeakyReLUFunctionBackward in one pass

@@ -20,6 +20,30 @@ def _modulated_weight(weight, style, scale, demodulate=True, transposed=False, e
     return w.reshape(b * o, i, kh, kw)
 
 
+def _modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, padding=1, eps=1e-8):
+    """The REFERENCE formulation (networks.py:233-282): materialise per-sample filters, grouped convolution.
+    Returns (out, None): demodulation is already inside the filters."""
+    b, cin, h, w = x.shape
+    cout = weight.shape[1]
+    wt = _modulated_weight(weight, style, scale, demodulate, transposed=upsample, eps=eps).type(x.dtype)
+    xin = x.reshape(1, b * cin, h, w)
+    if upsample:
+        out = F.conv_transpose2d(xin, wt, padding=0, stride=2, groups=b)
+    else:
+        out = F.conv2d(xin, wt, padding=padding, groups=b)
+    return out.view(b, cout, out.shape[2], out.shape[3]), None
+
+
+def _channel_scale(x, s):
+    return x * s.reshape(x.shape[0], x.shape[1], 1, 1).to(x.dtype)
+
+
+def _noise_bias_act(x, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5, row_scale=None):
+    if row_scale is not None:
+        x = _channel_scale(x, row_scale)
+    return _so.noise_bias_act_ref(x, noise, noise_weight, bias, negative_slope, scale)
+
+
 def _mipmap_warp(inputs, grid, max_num_levels=8, min_level=0.0, padding_mode="border"):
     out, aux = _smp.mipmap_warp_ref(inputs, grid, max_num_levels, min_level, padding_mode, return_aux=True)
     return out, aux["levels"]
@@ -43,11 +67,13 @@ def cpu_ops():
             name="cpu-oracle",
             upfirdn2d=_so.upfirdn2d_ref,
             fused_leaky_relu=_so.fused_leaky_relu_ref,
-            noise_bias_act=_so.noise_bias_act_ref,
+            noise_bias_act=_noise_bias_act,
             blur_noise_bias_act=_so.blur_noise_bias_act_ref,
             conv2d=F.conv2d,
             conv_transpose2d=F.conv_transpose2d,
             modulated_weight=_modulated_weight,
+            modulated_conv2d=_modulated_conv2d,
+            channel_scale=_channel_scale,
             mipmap_warp=_mipmap_warp,
             grid_sample=_smp.warp_ref,
             bilinear_downsample=_bilinear_downsample,

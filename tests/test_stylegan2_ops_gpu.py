@@ -285,3 +285,70 @@ def test_modulated_weight_tensor_core_demod(b, o, i, k, transposed, demod):
     (gs_ref,) = torch.autograd.grad((r2 * go).sum(), so_)
     (gs,) = torch.autograd.grad((out * go.to(DEV)).sum(), sg)
     assert_close(gs, gs_ref, rtol=2e-3, what="style gradient")
+
+
+@pytest.mark.parametrize("shape", [(3, 16, 64, 64), (2, 8, 4, 4), (2, 5, 33, 31), (1, 4, 256, 256)])
+def test_channel_scale_forward_backward(shape):
+    from gangealing_b200.op.modconv import channel_scale
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(*shape, generator=g)
+    s = torch.randn(shape[0], shape[1], generator=g)
+    go = torch.randn(*shape, generator=g)
+    xo, so_ = x.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    yo = xo * so_[:, :, None, None]
+    gxo, gso = torch.autograd.grad(yo, [xo, so_], go)
+    xg, sg = x.to(DEV).requires_grad_(True), s.to(DEV).requires_grad_(True)
+    y = channel_scale(xg, sg)
+    assert_close(y, yo, rtol=1e-6)
+    gx, gs = torch.autograd.grad(y, [xg, sg], go.to(DEV))
+    assert_close(gx, gxo, rtol=1e-6, what="gx")
+    assert_close(gs, gso, rtol=1e-4, what="gs")
+
+
+@pytest.mark.parametrize("b,cin,cout,h,upsample,k", [(3, 64, 32, 16, False, 3), (2, 32, 64, 8, True, 3), (2, 64, 3, 16, False, 1),
+                                                     (4, 128, 128, 32, False, 3)])
+def test_modulated_conv2d_dense_formulation_matches_the_grouped_reference(b, cin, cout, h, upsample, k):
+    """conv(W*s*d, x) (reference, grouped) == d * conv(W, x*s) (this repo, weight-shared), values and gradients."""
+    from gangealing_b200.op.modconv import channel_scale, modulated_conv2d
+    from oracle import opset
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator().manual_seed(b * cin)
+        w = torch.randn(1, cout, cin, k, k, generator=g)
+        x = torch.randn(b, cin, h, h, generator=g)
+        s = torch.randn(b, cin, generator=g) + 1.0
+        scale = 1.0 / (cin * k * k) ** 0.5
+        demod = k == 3
+        xo, so_ = x.clone().requires_grad_(True), s.clone().requires_grad_(True)
+        ref, none = opset.cpu_ops().modulated_conv2d(xo, w, so_, scale, demod, upsample, k // 2)
+        assert none is None
+        go = torch.randn(ref.shape, generator=g)
+        gxo, gso = torch.autograd.grad(ref, [xo, so_], go)
+        xg, sg = x.to(DEV).requires_grad_(True), s.to(DEV).requires_grad_(True)
+        raw, d = modulated_conv2d(xg, w.to(DEV), sg, scale, demod, upsample, k // 2)
+        out = channel_scale(raw, d) if d is not None else raw
+        assert_close(out, ref, rtol=1e-4, what="modulated conv")
+        gx, gs = torch.autograd.grad(out, [xg, sg], go.to(DEV))
+        assert_close(gx, gxo, rtol=2e-4, what="gx")
+        assert_close(gs, gso, rtol=2e-3, what="gstyle")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_noise_bias_act_with_row_scale():
+    op = _ops()
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 6, 16, 16, generator=g)
+    noise = torch.randn(2, 1, 16, 16, generator=g)
+    nw, b, rs = torch.randn(1, generator=g), torch.randn(6, generator=g), torch.rand(2, 6, generator=g) + 0.5
+    go = torch.randn(2, 6, 16, 16, generator=g)
+    leaves_o = [t.clone().requires_grad_(True) for t in (x, rs)]
+    yo = so.noise_bias_act_ref(leaves_o[0] * leaves_o[1][:, :, None, None], noise, nw, b)
+    go_x, go_rs = torch.autograd.grad(yo, leaves_o, go)
+    xg, rsg = x.to(DEV).requires_grad_(True), rs.to(DEV).requires_grad_(True)
+    y = op.noise_bias_act(xg, noise.to(DEV), nw.to(DEV), b.to(DEV), row_scale=rsg)
+    assert_close(y, yo, rtol=1e-5)
+    gx, grs = torch.autograd.grad(y, [xg, rsg], go.to(DEV))
+    assert_close(gx, go_x, rtol=1e-5, what="gx")
+    assert_close(grs, go_rs, rtol=1e-4, what="g row_scale")
