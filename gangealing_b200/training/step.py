@@ -86,10 +86,21 @@ class Trainer:
         requires_grad(self.t_ema, False)
         self.t_module, self.ll_module = self.stn, self.ll
         if distributed:
-            ids = [torch.cuda.current_device()] if device != "cpu" and torch.device(device).type == "cuda" else None
-            self.stn = nn.parallel.DistributedDataParallel(self.stn, device_ids=ids, broadcast_buffers=False,
-                                                           gradient_as_bucket_view=True)
-            self.ll = nn.parallel.DistributedDataParallel(self.ll, device_ids=ids, broadcast_buffers=False)
+            on_gpu = device != "cpu" and torch.device(device).type == "cuda"
+            ids = [torch.cuda.current_device()] if on_gpu else None
+
+            def wrap():
+                self.stn = nn.parallel.DistributedDataParallel(self.stn, device_ids=ids, broadcast_buffers=False,
+                                                               gradient_as_bucket_view=True)
+                self.ll = nn.parallel.DistributedDataParallel(self.ll, device_ids=ids, broadcast_buffers=False)
+            if on_gpu:  # built on a side stream so the wrapped step can later be captured into a CUDA graph
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    wrap()
+                torch.cuda.current_stream().wait_stream(side)
+            else:
+                wrap()
         fused = torch.device(device).type == "cuda"
         # capturable: the optimiser state lives on the device so a whole iteration can be replayed as a CUDA graph
         self.t_optim = optim.Adam(self.t_module.parameters(), lr=cfg.stn_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused,
@@ -135,9 +146,10 @@ class Trainer:
 
         The reference's loop is launch-bound at its recipe's per-GPU batch (thousands of launches per step,
         SURVEY.md 8e "scaling risk"); every op on this path is graph-safe: static shapes, no host sync (the fused
-        sampler drops MipmapWarp's `.item()`), device-side RNG and optimiser state.  Single-process only."""
+        sampler drops MipmapWarp's `.item()`), device-side RNG and optimiser state.  Under DDP the NCCL bucket
+        all-reduces and the loss reduce are captured as graph nodes too."""
         if self.distributed:
-            raise RuntimeError("capture() is for single-process runs; DDP steps run eagerly")
+            warmup = max(warmup, 11)  # DDP needs >= 11 eager iterations on the side stream before capture (PyTorch docs)
         cfg = self.cfg
         self._static_z = torch.randn(cfg.batch, cfg.dim_latent, device=self.device)
         side = torch.cuda.Stream()
