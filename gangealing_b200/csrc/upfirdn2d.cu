@@ -192,9 +192,8 @@ __device__ __forceinline__ void issue_item(const T* in, const BandParams& p, int
                                            ItemS* pub) {
   const Item it = item_geom(p, item, sizeof(T));
   pub->it = it;
-  if (it.nreal <= 0) {   // padding-only band: nothing to copy, but the stage's phase must still complete
+  if (it.nreal <= 0) {
     for (int pl = 0; pl < it.n_planes; ++pl) pub->v0[pl] = it.d0 - it.vrows * p.in_w;
-    mbar_expect_tx(bar, 0);
     return;
   }
   uint32_t total = 0;
@@ -298,28 +297,6 @@ __device__ __forceinline__ void lane_strip(T* __restrict__ out_plane, const T* _
 // loop is straight-line FMA code: no row/column tests, shuffles, selects or per-value address arithmetic.
 // Out-of-range columns are handled by folding a 0/1 mask into per-lane horizontal weights (the elements they
 // touch are real neighbours or zero-filled guards, hence finite).
-// packed fp32x2 math (Blackwell FFMA2 / FMUL2): one issue slot for two lanes of the vertical pass and epilogue
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t mov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t"
-      "mul.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-
 template <int IW4, int S0, bool FUSED, bool VEC>
 struct StripF32 {
   float* __restrict__ out_ptr;        // &out[plane][oys][x0]
@@ -328,10 +305,9 @@ struct StripF32 {
   const float (&ku)[4];
   float wgt[kCO][4];
   float4 nz[kRS];
-  float2 hw[4][kCO / 2];       // horizontal results of the last 4 input rows, as fp32x2 pairs
+  float hw[4][kCO];
   int nrow, x0;
-  float2 ku2[4];               // vertical taps, broadcast pairs
-  float2 rs2, bc2, nw2, neg2;  // epilogue constants (already multiplied by the positive gain), broadcast pairs
+  float rs, bc, nw, gpos, gdiff;
   bool has_noise;
 
   template <int R>
@@ -342,39 +318,36 @@ struct StripF32 {
     float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (SH >= 2) q2 = qp[2];                     // inputs SH .. SH+6 reach the third quad only when SH >= 2
     const float Q[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-    float h[kCO];
 #pragma unroll
     for (int j = 0; j < kCO; ++j)
-      h[j] = fmaf(wgt[j][3], Q[SH + j + 3],
-                  fmaf(wgt[j][2], Q[SH + j + 2], fmaf(wgt[j][1], Q[SH + j + 1], wgt[j][0] * Q[SH + j])));
-    hw[R & 3][0] = make_float2(h[0], h[1]);
-    hw[R & 3][1] = make_float2(h[2], h[3]);
+      hw[R & 3][j] = fmaf(wgt[j][3], Q[SH + j + 3],
+                          fmaf(wgt[j][2], Q[SH + j + 2], fmaf(wgt[j][1], Q[SH + j + 1], wgt[j][0] * Q[SH + j])));
     if (R >= 3) {
       constexpr int RO = R >= 3 ? R - 3 : 0;
-      float2 acc[kCO / 2];
+      float acc[kCO];
 #pragma unroll
-      for (int jp = 0; jp < kCO / 2; ++jp) {
-        acc[jp] = ffma2(ku2[3], hw[(RO + 3) & 3][jp],
-                        ffma2(ku2[2], hw[(RO + 2) & 3][jp], ffma2(ku2[1], hw[(RO + 1) & 3][jp], fmul2(ku2[0], hw[RO & 3][jp]))));
+      for (int j = 0; j < kCO; ++j) {
+        acc[j] = fmaf(ku[3], hw[(RO + 3) & 3][j],
+                      fmaf(ku[2], hw[(RO + 2) & 3][j], fmaf(ku[1], hw[(RO + 1) & 3][j], ku[0] * hw[RO & 3][j])));
         if (FUSED) {
-          // t' = gain*(rs*acc + bias + nw*noise);  lrelu*gain = t' + (alpha - 1)*min(t', 0)
-          float2 t = ffma2(acc[jp], rs2, bc2);
+          float t = fmaf(acc[j], rs, bc);
           if (has_noise) {
             const float4 nv4 = nz[RO < kRS ? RO : 0];
-            t = ffma2(nw2, jp == 0 ? make_float2(nv4.x, nv4.y) : make_float2(nv4.z, nv4.w), t);
+            const float nv = j == 0 ? nv4.x : (j == 1 ? nv4.y : (j == 2 ? nv4.z : nv4.w));
+            t = fmaf(nw, nv, t);
           }
-          acc[jp] = ffma2(neg2, make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f)), t);
+          // lrelu(t)*scale = scale*t + (alpha*scale - scale)*min(t, 0): one ALU op + two FMA-pipe ops
+          acc[j] = fmaf(gdiff, fminf(t, 0.f), gpos * t);
         }
       }
       if (RO < nrow) {
         float* op = out_ptr + static_cast<int64_t>(RO) * p.out_w;
         if (VEC) {
-          *reinterpret_cast<float4*>(op) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+          *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         } else {
-          const float a4[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};
 #pragma unroll
           for (int j = 0; j < kCO; ++j)
-            if (x0 + j < p.out_w) op[j] = a4[j];
+            if (x0 + j < p.out_w) op[j] = acc[j];
         }
       }
     }
@@ -393,15 +366,8 @@ __device__ __forceinline__ void lane_strip_f32(float* __restrict__ out_plane, co
                                                float rs, float bc, float nw) {
   StripF32<IW4, S0, FUSED, VEC> st{out_plane + static_cast<int64_t>(oys) * p.out_w + x0, row_ptr, p, ku};
   st.nrow = nrow; st.x0 = x0;
-  st.has_noise = FUSED && noise_plane != nullptr;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) st.ku2[a] = make_float2(ku[a], ku[a]);
-  const float gain = p.scale;   // > 0 on every call site (sqrt(2)); a non-positive gain takes the generic path
-  st.rs2 = make_float2(rs * gain, rs * gain);
-  st.bc2 = make_float2(bc * gain, bc * gain);
-  st.nw2 = make_float2(nw * gain, nw * gain);
-  const float neg = (p.act == 3) ? p.alpha - 1.f : 0.f;
-  st.neg2 = make_float2(neg, neg);
+  st.rs = rs; st.bc = bc; st.nw = nw; st.has_noise = FUSED && noise_plane != nullptr;
+  st.gpos = p.scale; st.gdiff = (p.act == 3) ? p.alpha * p.scale - p.scale : 0.f;
   const int colbase = x0 - p.pad_x0;
 #pragma unroll
   for (int j = 0; j < kCO; ++j)
@@ -439,7 +405,6 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[kStages];
   __shared__ ItemS pub[kStages];
-  __shared__ int done_cnt[kStages];
   T* stage_base = reinterpret_cast<T*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -452,11 +417,10 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
   __syncthreads();
 
   const int64_t stride = gridDim.x;
-  // prologue: fill all stages (issued before the tap set-up below so the copies fly meanwhile)
+  // prologue: fill kStages-1 stages (issued before the tap set-up below so the copies fly meanwhile)
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      done_cnt[s] = 0;
+    for (int s = 0; s < kStages - 1; ++s) {
       const int64_t it = blockIdx.x + s * stride;
       if (it < n_items) issue_item(in, p, it, stage_base + static_cast<int64_t>(s) * p.stage_elems, &full_bar[s], &pub[s]);
     }
@@ -512,7 +476,7 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
 
   float nw = 0.f;
   if (FUSED) nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
-  __syncthreads();  // done_cnt / barriers / prologue state visible to every warp; the ONLY CTA-wide barrier
+  __syncthreads();  // the prologue's published item geometry is visible to every thread
 
   // strip geometry: `full_x` strips of lx lanes x 4 columns, plus one narrower tail strip whose lanes
   // are folded down the rows instead (so 129- or 65-wide outputs do not pay for a second full strip)
@@ -522,17 +486,39 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
   int lt_log2 = 0;
   while ((1 << lt_log2) * kCO < tail_w) ++lt_log2;
 
-  // Warps are DECOUPLED: each one waits for a stage's data (mbarrier), works through its own tasks of that item and
-  // checks out on a per-stage counter; the last warp to check out refills the stage with the item three ahead.
-  // No CTA-wide barrier in the loop: a fast warp runs ahead into the next (already resident) stages.
-  int k = 0;                // local item counter (identical sequence in every warp)
+  uint32_t phase_bits = 0;  // bit s: parity the next wait on stage s must observe
+  int k = 0;                // local iteration counter
   for (int64_t item = blockIdx.x; item < n_items; item += stride, ++k) {
     const int stage = k % kStages;
-    mbar_wait(&full_bar[stage], static_cast<uint32_t>(k / kStages) & 1u);
-    const Item it = pub[stage].it;   // published by the producer before it armed the barrier (release/acquire)
+    // prefetch the item kStages-1 ahead into the stage freed by the previous iteration
+    if (tid == 0) {
+      const int64_t nxt = item + (kStages - 1) * stride;
+      if (nxt < n_items) {
+        const int ns = (k + kStages - 1) % kStages;
+        issue_item(in, p, nxt, stage_base + static_cast<int64_t>(ns) * p.stage_elems, &full_bar[ns], &pub[ns]);
+      }
+    }
+    // geometry published by the producer (visible: written before the previous iteration's / the prologue's barrier)
+    const Item& it = pub[stage].it;
+    if (it.nreal > 0) {  // a padding-only band issues no transfer, so its stage's phase does not advance
+      mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
+      phase_bits ^= 1u << stage;
+    }
     T* stage_ptr = stage_base + static_cast<int64_t>(stage) * p.stage_elems;   // 16-byte aligned
-    const int n_top = it.nreal > 0 ? it.lo - it.vy0 : it.vrows;                // zero rows above the image
-    const int first_bot = it.nreal > 0 ? n_top + it.nreal : it.vrows;          // first zero row below it
+    // zero padding rows above / below the image (first / last band of a plane only)
+    const int n_top = it.nreal > 0 ? it.lo - it.vy0 : it.vrows;
+    const int n_bot = it.nreal > 0 ? it.vrows - n_top - it.nreal : 0;
+    if (n_top > 0 || n_bot > 0) {
+      for (int pl = 0; pl < it.n_planes; ++pl) {
+        T* slot = stage_ptr + static_cast<int64_t>(pl) * p.slot_elems;
+        const int v0 = pub[stage].v0[pl];
+        const int first_real = v0 + n_top * p.in_w;
+        const int after_real = first_real + max(it.nreal, 0) * p.in_w;
+        for (int e = v0 + tid; e < first_real; e += kBandThreads) slot[e] = Cvt<T>::from_f(0.f);
+        for (int e = after_real + tid; e < v0 + it.vrows * p.in_w; e += kBandThreads) slot[e] = Cvt<T>::from_f(0.f);
+      }
+      __syncthreads();
+    }
 
     const int sy_main = (it.rows + (32 >> p.lx_log2) * kRS - 1) / ((32 >> p.lx_log2) * kRS);
     const int main_tasks = full_x * sy_main;
@@ -552,20 +538,6 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
         xs = full_x * lx_main * kCO;
         lg = lt_log2;
       }
-      T* slot = stage_ptr + static_cast<int64_t>(pl) * p.slot_elems;
-      const int v0 = pub[stage].v0[pl];
-      // ---- zero padding rows (first / last band of a plane): this warp clears the part its own task reads
-      if (n_top > 0 || first_bot < it.vrows) {
-        const int vr_lo = sy * (32 >> lg) * kRS;                              // task's first virtual row (band-relative)
-        const int vr_hi = min(vr_lo + (32 >> lg) * kRS + 3, it.vrows);        // one past its last
-        const int c_lo = max(xs - p.pad_x0, 0);
-        const int c_hi = min(xs - p.pad_x0 + (kCO << lg) + 3, p.in_w);
-        for (int vr = vr_lo; vr < vr_hi; ++vr) {
-          if (vr >= n_top && vr < first_bot) continue;                        // a real row
-          for (int c = c_lo + lane; c < c_hi; c += 32) slot[v0 + vr * p.in_w + c] = Cvt<T>::from_f(0.f);
-        }
-        __syncwarp();
-      }
       const int lane_x = lane & ((1 << lg) - 1);
       const int lane_y = lane >> lg;
       const int64_t m = it.m0 + pl;
@@ -583,9 +555,11 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
         if (noise) noise_plane = noise + n * p.out_h * static_cast<int64_t>(p.out_w);
       }
       T* out_plane = out + m * p.out_h * static_cast<int64_t>(p.out_w);
+      T* slot = stage_ptr + static_cast<int64_t>(pl) * p.slot_elems;
+      const int v0 = pub[stage].v0[pl];
       // The 3 elements in front of the first virtual row and behind the last one are foreign (alignment
       // prefix / suffix of the copy, or never written): only the lanes below ever touch them (with zero
-      // weight), so those lanes make them finite zeros themselves -- no barrier needed.
+      // weight), so those lanes make them finite zeros themselves -- no extra barrier.
       if (x0 == 0 && oys == it.oy0) {
 #pragma unroll
         for (int e = 1; e <= 3; ++e) slot[v0 - e] = Cvt<T>::from_f(0.f);
@@ -596,7 +570,7 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
         for (int e = 0; e < 3; ++e) slot[vend + e] = Cvt<T>::from_f(0.f);
       }
       if constexpr (sizeof(T) == 4 && IW4 >= 0) {
-        if (sep && (!FUSED || p.scale > 0.f)) {
+        if (sep) {
           const int pos0 = v0 + (oys - p.pad_y0 - it.vy0) * p.in_w + (x0 - p.pad_x0);
           const float* row_ptr = reinterpret_cast<const float*>(slot) + pos0;
 #define GG_STRIP(S0_, V_)                                                                                    \
@@ -627,17 +601,7 @@ fir4_band_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __r
       else
         lane_strip<T, false, FUSED>(out_plane, slot + v0, it.vy0, noise_plane, p, kf, ku, kv, oys, nrow, x0, rs, bc, nw);
     }
-    // ---- check out of this stage; the last warp refills it
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      const int old = atomicAdd(&done_cnt[stage], 1);
-      if (old == kBandWarps - 1) {
-        done_cnt[stage] = 0;
-        const int64_t nxt = item + static_cast<int64_t>(kStages) * stride;
-        if (nxt < n_items) issue_item(in, p, nxt, stage_ptr, &full_bar[stage], &pub[stage]);
-      }
-    }
+    __syncthreads();  // every warp is done with `stage` (and its published geometry) before it is refilled
   }
 }
 
