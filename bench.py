@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("GG_BENCH_BATCH", "16")), help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("GG_BENCH_BATCH", "32")), help="per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="single-GPU: run the step eagerly instead of as a CUDA graph")
@@ -220,6 +220,7 @@ def run_ours(args):
     if rank != 0:
         if distributed:
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     images = args.batch * world * args.steps
@@ -254,9 +255,10 @@ def run_ours(args):
             "gpu_launches": calls, "roofline": roof, "cpu_baseline": cpu,
             "clocks": sampler.summary() if sampler else None,
             "losses": {k: float(v.detach()) for k, v in out.items()}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
