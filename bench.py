@@ -89,11 +89,16 @@ def workload_config(args):
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
+def cpu_threads():
+    """All host cores, capped at 64: beyond that ATen's intra-op threading of these small convolutions gets slower."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("GG_CPU_THREADS", "64"))))
+
+
 def cpu_step_rate(batch, steps=1, warmup=0):
     """The reference algorithm (oracle port: same host code, CPU op set) on all host cores -> images/s."""
     from oracle import opset
     from gangealing_b200.training import TrainConfig, Trainer
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     cfg = TrainConfig(batch=batch)
     tr = Trainer(cfg, "cpu", ops=opset.cpu_ops())
     for _ in range(warmup):
@@ -110,7 +115,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     steps = max(1, min(args.steps, 2))  # bounded sample: each CPU step of B=2 takes ~10-20 s
     warm = 1 if args.warmup > 0 else 0
     rate, sec = cpu_step_rate(args.cpu_batch, steps=steps, warmup=warm)
@@ -188,11 +193,16 @@ def run_ours(args):
         sampler.start()
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    profile = os.environ.get("GG_PROFILE") == "1"   # `ncu --profile-from-start off`: capture the timed steps only
+    if profile:
+        torch.cuda.cudart().cudaProfilerStart()
     st.record()
     for _ in range(args.steps):
         out = tr.step()
     en.record()
     sync_all()
+    if profile:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = st.elapsed_time(en)
     calls = calls_per_step * args.steps
     if sampler:
@@ -243,10 +253,11 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             rate, sec = cpu_step_rate(args.cpu_batch, steps=1, warmup=0)
-            cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                   "sample": "1 step of per-step batch %d on %d host threads (%.1f s)" % (args.cpu_batch, os.cpu_count(), sec)}
+            cpu = {"value": rate, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                   "sample": "1 step of per-step batch %d on %d host threads of %d cores (%.1f s)" % (
+                       args.cpu_batch, cpu_threads(), os.cpu_count(), sec)}
         except Exception as exc:  # the baseline must never take the bench down
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (exc,)}
+            cpu = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": "failed: %r" % (exc,)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),

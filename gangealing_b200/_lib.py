@@ -39,6 +39,11 @@ SIGNATURES = {
     "gg_modconv_wsq": (_I, [_P, _P, _I, _I, _I, _P]),
     "gg_modconv_demod": (_I, [_P, _P, _P, _F, _F, _I, _I, _I, _P]),
     "gg_modconv_modulate": (_I, [_P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P]),
+    "gg_noise_bias_act_nhwc": (_I, [_P] * 6 + [_F, _F, _L, _I, _L, _P]),
+    "gg_nhwc_rowwise_workspace": (_L, [_L, _I, _L]),
+    "gg_channel_scale_nhwc": (_I, [_P] * 6 + [_L, _I, _L, _P]),
+    "gg_bias_act_backward_nhwc": (_I, [_P] * 5 + [_F, _F, _L, _I, _L, _P]),
+    "gg_blur_nhwc": (_I, [_P] * 7 + [_L] + [_I] * 12 + [_F, _F, _P]),
     "gg_splat2d_workspace": (_L, [_L, _I, _I, _I]),
     "gg_splat2d_forward": (_I, [_P] * 6 + [_L, _L, _I, _I, _I, _I, _P]),
     "gg_flow_compose_forward": (_I, [_P] * 7 + [_L, _I, _I, _I, _P]),
@@ -96,6 +101,33 @@ def require_cuda(*tensors):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def is_nhwc(t):
+    """True for a 4-D fp32 tensor stored channels-last (and not also plain-contiguous)."""
+    return (t.dim() == 4 and t.dtype == torch.float32 and t.shape[1] > 1 and t.shape[2] * t.shape[3] > 1
+            and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous())
+
+
+_sep_cache = {}
+
+
+def filter_is_separable(kernel):
+    """Rank-1 test of a (<=4x4) FIR filter, cached per (storage, version): one host read per distinct filter."""
+    key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
+    v = _sep_cache.get(key)
+    if v is None:
+        k = kernel.detach().float().cpu()
+        big = k.abs().max()
+        if big == 0:
+            v = True
+        else:
+            i0, j0 = divmod(int(k.abs().argmax()), k.shape[1])
+            v = bool((k - torch.outer(k[:, j0], k[i0, :]) / k[i0, j0]).abs().max() <= 1e-6 * big)
+        if len(_sep_cache) > 64:
+            _sep_cache.clear()
+        _sep_cache[key] = v
+    return v
 
 
 def stream():

@@ -1,0 +1,494 @@
+// nhwc.cu -- channels-last (N, H, W, C) variants of the StyledConv tail family (sm_100a).
+//
+// Why: cuDNN's tensor-core convolution kernels are NHWC-native; with NCHW activations every convolution of the step
+// is bracketed by nchwToNhwc / nhwcToNchw conversion kernels (22 % of the step in profiles/r01_step_launches_b8).
+// Keeping the generator's activations channels-last end to end removes them -- provided the hand-written kernels
+// between the convolutions speak NHWC too.  In this layout a pixel's channels are contiguous, so with C % 4 == 0
+// EVERYTHING is 16-byte aligned: the blur can use a real 4-D TMA tensor map (cp.async.bulk.tensor, SASS UTMALDG)
+// whose out-of-bounds zero fill implements the padding of upfirdn2d for free.
+//
+// Same math / reference citations as the NCHW kernels (bias_act.cu, upfirdn2d.cu):
+//   gg_noise_bias_act_nhwc       lrelu(rs[n,c]*x + nw*noise[n,p] + b[c])*gain                networks.py:291-298,346-348
+//   gg_bias_act_backward_nhwc    gx = (out>0 ? g : a*g)*gain ; grad_bias[c] = sum gx          op/fused_act.py:20-38
+//   gg_channel_scale_nhwc        x*s[n,c] (+ row_dot[n,c] = sum_p x*y)                        networks.py:236,243
+//   gg_blur_nhwc                 upfirdn2d(up=down=1, <=4x4 separable or not) [+ fused tail]   networks.py:266 (+346-348)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gg {
+namespace {
+
+constexpr int kT = 256;
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void __launch_bounds__(kT)
+noise_bias_act_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ noise,
+                           const float* __restrict__ noise_weight, const float* __restrict__ bias,
+                           const float* __restrict__ row_scale, float alpha, float gain, int64_t n_vec, int c4,
+                           int64_t hw) {
+  const float nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
+  const int64_t base = (static_cast<int64_t>(blockIdx.x) * 4) * kT + threadIdx.x;
+  Vec16<float> xv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t v = base + static_cast<int64_t>(u) * kT;
+    if (v < n_vec) xv[u] = ld_vec_stream(x + v * 4);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t v = base + static_cast<int64_t>(u) * kT;
+    if (v < n_vec) {
+      const int64_t pix = v / c4;                      // n*hw + p
+      const int cq = static_cast<int>(v - pix * c4);
+      const int64_t n = pix / hw;
+      const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 r = row_scale ? __ldg(reinterpret_cast<const float4*>(row_scale + n * c4 * 4) + cq)
+                                 : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float nz = noise ? nw * __ldg(noise + pix) : 0.f;
+      const float bb[4] = {b.x, b.y, b.z, b.w}, rr[4] = {r.x, r.y, r.z, r.w};
+      Vec16<float> o;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float t = fmaf(xv[u].v[k], rr[k], bb[k]) + nz;
+        o.v[k] = (t > 0.f ? t : t * alpha) * gain;
+      }
+      st_vec_stream(out + v * 4, o);
+    }
+  }
+}
+
+// One CTA = `rows` consecutive pixels of one sample x all channels.  Thread = (channel quad, pixel lane); per-channel
+// sums are reduced across the CTA's pixel lanes in shared memory and written as one partial row per CTA.
+// MODE 0: channel_scale (out = x*s, dot = sum x*y)   MODE 1: bias_act backward (out = act'(ref)*x*gain, dot = sum out)
+template <int MODE>
+__global__ void __launch_bounds__(kT)
+rowwise_nhwc_kernel(float* __restrict__ out, float* __restrict__ partial, const float* __restrict__ x,
+                    const float* __restrict__ y, const float* __restrict__ s, float alpha, float gain, int c4,
+                    int64_t hw, int chunk, int chunks_per_sample) {
+  extern __shared__ float red[];                       // [pixel lanes][C] partial sums
+  const int64_t n = blockIdx.x / chunks_per_sample;
+  const int ck = blockIdx.x - n * chunks_per_sample;
+  const int64_t p0 = static_cast<int64_t>(ck) * chunk, p1 = min(p0 + chunk, hw);
+  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;       // pixel lanes when C/4 <= 256
+  float4 acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // a thread owns channel quads cq = tid % c4 (+ k*kT when c4 > kT is not supported: C <= 1024)
+  const int cq = threadIdx.x % c4;
+  const int pl = threadIdx.x / c4;
+  if (pl < lanes_p) {
+    float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (MODE == 0) sv = __ldg(reinterpret_cast<const float4*>(s + n * c4 * 4) + cq);
+    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
+      const int64_t off = ((n * hw + p) * c4 + cq) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(x + off);
+      float4 o;
+      if (MODE == 0) {
+        o = make_float4(xv.x * sv.x, xv.y * sv.y, xv.z * sv.z, xv.w * sv.w);
+        if (y) {
+          const float4 yv = *reinterpret_cast<const float4*>(y + off);
+          acc[0].x = fmaf(xv.x, yv.x, acc[0].x); acc[0].y = fmaf(xv.y, yv.y, acc[0].y);
+          acc[0].z = fmaf(xv.z, yv.z, acc[0].z); acc[0].w = fmaf(xv.w, yv.w, acc[0].w);
+        }
+      } else {
+        const float4 rv = *reinterpret_cast<const float4*>(y + off);   // y = saved forward output
+        o.x = (rv.x > 0.f ? xv.x : xv.x * alpha) * gain; o.y = (rv.y > 0.f ? xv.y : xv.y * alpha) * gain;
+        o.z = (rv.z > 0.f ? xv.z : xv.z * alpha) * gain; o.w = (rv.w > 0.f ? xv.w : xv.w * alpha) * gain;
+        acc[0].x += o.x; acc[0].y += o.y; acc[0].z += o.z; acc[0].w += o.w;
+      }
+      *reinterpret_cast<float4*>(out + off) = o;
+    }
+  }
+  if (partial) {
+    float4* r4 = reinterpret_cast<float4*>(red);
+    if (pl < lanes_p) r4[pl * c4 + cq] = acc[0];
+    __syncthreads();
+    if (threadIdx.x < c4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int l = 0; l < lanes_p; ++l) {
+        const float4 v = r4[l * c4 + threadIdx.x];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      reinterpret_cast<float4*>(partial + static_cast<int64_t>(blockIdx.x) * c4 * 4)[threadIdx.x] = t;
+    }
+  }
+}
+
+// dst[r][c] = sum_k partial[(r*K + k)][c]    (r = sample for channel_scale; a single row for grad_bias)
+__global__ void nhwc_finish_kernel(float* __restrict__ dst, const float* __restrict__ partial, int64_t rows, int K, int C) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int64_t r = i / C;
+  const int c = static_cast<int>(i - r * C);
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += partial[(r * K + k) * C + c];
+  dst[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ blur (TMA tiled)
+constexpr int kCB = 32;     // channels per CTA (128 B per pixel in the tile)
+constexpr int kBX = 64;     // output columns per CTA; a thread owns 2 adjacent columns x 4 channels
+constexpr int kRY = 4;      // input rows per pipeline stage
+constexpr int kNS = 3;      // stages
+constexpr int kTileW = kBX + 3;
+constexpr int kStageFloats = kRY * kTileW * kCB;
+
+struct BlurNhwcParams {
+  int n, c, in_h, in_w, out_h, out_w;
+  int pad_x0, pad_y0;
+  int seg_rows;             // output rows per CTA (grid.y segments)
+  int act;                  // FUSED: 1 linear, 3 lrelu
+  float alpha, gain;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int x0, int y0, int n0,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(x0), "r"(y0), "r"(n0), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// CTA = (sample n, 64-column block, 32-channel chunk, row segment).  Input rows stream through a 3-stage ring of
+// {32 ch x 67 px x 4 rows} TMA boxes (zero-filled outside the image = upfirdn2d's padding); each thread slides a
+// 4-row window of horizontal results for its 2 columns x 4 channels down the whole segment, so a row is read from
+// shared memory once and from HBM once (+3 halo rows per segment, +3/64 halo columns).
+template <bool FUSED, bool SEP>
+__global__ void __launch_bounds__(kT, 2)
+blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tmap, const float* __restrict__ filt,
+                 int kh, int kw, const float* __restrict__ noise, const float* __restrict__ noise_weight,
+                 const float* __restrict__ bias, const float* __restrict__ row_scale, BlurNhwcParams p) {
+  extern __shared__ __align__(128) float tiles[];
+  __shared__ uint64_t full_bar[kNS];
+  const int tid = threadIdx.x;
+  const int cq = tid & 7;                 // channel quad within the 32-channel chunk
+  const int xg = tid >> 3;                // 0..31 -> columns 2*xg, 2*xg+1 of the block
+  const int chunks = p.c / kCB;
+  const int bx = blockIdx.x / chunks, cc = blockIdx.x - bx * chunks;
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * p.seg_rows;
+  const int rows_out = min(p.seg_rows, p.out_h - oy0);
+  const int x_out0 = bx * kBX;            // first output column of the block
+  const int c0 = cc * kCB;
+  // input row/col of tap (0,0) for output (oy0, x_out0)
+  const int iy0 = oy0 - p.pad_y0, ix0 = x_out0 - p.pad_x0;
+  const int rows_in = rows_out + 3;
+  const int n_stage_iters = (rows_in + kRY - 1) / kRY;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kNS; ++s) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kNS - 1; ++s)
+      if (s < n_stage_iters) {
+        mbar_expect_tx(&full_bar[s], kStageFloats * 4);
+        tma_load_4d(tiles + s * kStageFloats, &tmap, c0, ix0, iy0 + s * kRY, n, &full_bar[s]);
+      }
+  }
+
+  // taps (flipped: true convolution), rank-1 factorisation when possible
+  float kf[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      kf[a][b] = (a < kh && b < kw) ? __ldg(filt + (kh - 1 - a) * kw + (kw - 1 - b)) : 0.f;
+  float ku[4], kv[4];
+  {
+    int a0 = 0, b0 = 0;
+    float big = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (fabsf(kf[a][b]) > big) { big = fabsf(kf[a][b]); a0 = a; b0 = b; }
+    float piv = 1.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (a == a0 && b == b0) piv = kf[a][b];
+    const float inv = big > 0.f ? 1.f / piv : 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float col = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) if (b == b0) col = kf[a][b];
+      ku[a] = col * inv;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      float row = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) if (a == a0) row = kf[a][b];
+      kv[b] = row;
+    }
+  }
+
+  // per-thread channel constants (a thread keeps its 4 channels for the whole segment)
+  float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = make_float4(1.f, 1.f, 1.f, 1.f);
+  float nw = 0.f;
+  if (FUSED) {
+    if (bias) bq = __ldg(reinterpret_cast<const float4*>(bias + c0) + cq);
+    if (row_scale) rq = __ldg(reinterpret_cast<const float4*>(row_scale + static_cast<int64_t>(n) * p.c + c0) + cq);
+    nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
+  }
+  const int xo = x_out0 + 2 * xg;         // first of this thread's two output columns
+  const bool ok0 = xo < p.out_w, ok1 = xo + 1 < p.out_w;
+
+  // window: sep -> horizontal results hw[4 rows][2 cols] (float4 over channels); else raw inputs rw[4 rows][5 cols]
+  float4 hw[SEP ? 4 : 1][2];
+  float4 rw[SEP ? 1 : 4][5];
+  int r_in = 0;                            // input rows consumed so far (relative to iy0)
+  for (int it = 0; it < n_stage_iters; ++it) {
+    const int stage = it % kNS;
+    if (tid == 0) {
+      const int nxt = it + kNS - 1;
+      if (nxt < n_stage_iters) {
+        const int ns = nxt % kNS;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full_bar[ns], kStageFloats * 4);
+        tma_load_4d(tiles + ns * kStageFloats, &tmap, c0, ix0, iy0 + nxt * kRY, n, &full_bar[ns]);
+      }
+    }
+    mbar_wait(&full_bar[stage], static_cast<uint32_t>((it / kNS) & 1));
+    const float* st = tiles + stage * kStageFloats;
+#pragma unroll
+    for (int rr = 0; rr < kRY; ++rr, ++r_in) {
+      // 5 input pixels (columns 2xg .. 2xg+4 of the tile) x 4 channels of this thread
+      const float4* rowp = reinterpret_cast<const float4*>(st + (rr * kTileW + 2 * xg) * kCB) + cq;
+      float4 q[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) q[i] = rowp[i * (kCB / 4)];
+      if constexpr (SEP) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float4 h;
+          h.x = fmaf(kv[3], q[j + 3].x, fmaf(kv[2], q[j + 2].x, fmaf(kv[1], q[j + 1].x, kv[0] * q[j].x)));
+          h.y = fmaf(kv[3], q[j + 3].y, fmaf(kv[2], q[j + 2].y, fmaf(kv[1], q[j + 1].y, kv[0] * q[j].y)));
+          h.z = fmaf(kv[3], q[j + 3].z, fmaf(kv[2], q[j + 2].z, fmaf(kv[1], q[j + 1].z, kv[0] * q[j].z)));
+          h.w = fmaf(kv[3], q[j + 3].w, fmaf(kv[2], q[j + 2].w, fmaf(kv[1], q[j + 1].w, kv[0] * q[j].w)));
+          hw[rr][j] = h;                   // kRY == 4: slot rr == r_in & 3
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) rw[rr][i] = q[i];
+      }
+      const int ro = r_in - 3;             // output row (relative to oy0) completed by this input row
+      if (ro >= 0 && ro < rows_out) {
+        const int oy = oy0 + ro;
+        float4 acc[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (SEP) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const float4 h = hw[(rr + 1 + a) & 3][j];   // rows r_in-3 .. r_in in order
+              a4.x = fmaf(ku[a], h.x, a4.x); a4.y = fmaf(ku[a], h.y, a4.y);
+              a4.z = fmaf(ku[a], h.z, a4.z); a4.w = fmaf(ku[a], h.w, a4.w);
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const float4 v = rw[(rr + 1 + a) & 3][j + b];
+                a4.x = fmaf(kf[a][b], v.x, a4.x); a4.y = fmaf(kf[a][b], v.y, a4.y);
+                a4.z = fmaf(kf[a][b], v.z, a4.z); a4.w = fmaf(kf[a][b], v.w, a4.w);
+              }
+          }
+          acc[j] = a4;
+        }
+        if (FUSED) {
+          float nz0 = 0.f, nz1 = 0.f;
+          if (noise) {
+            const float* np_ = noise + (static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + xo;
+            if (ok0) nz0 = nw * __ldg(np_);
+            if (ok1) nz1 = nw * __ldg(np_ + 1);
+          }
+          const float neg = (p.act == 3) ? p.alpha : 1.f;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float nzj = j ? nz1 : nz0;
+            float t;
+            t = fmaf(acc[j].x, rq.x, bq.x) + nzj; acc[j].x = (t > 0.f ? t : t * neg) * p.gain;
+            t = fmaf(acc[j].y, rq.y, bq.y) + nzj; acc[j].y = (t > 0.f ? t : t * neg) * p.gain;
+            t = fmaf(acc[j].z, rq.z, bq.z) + nzj; acc[j].z = (t > 0.f ? t : t * neg) * p.gain;
+            t = fmaf(acc[j].w, rq.w, bq.w) + nzj; acc[j].w = (t > 0.f ? t : t * neg) * p.gain;
+          }
+        }
+        float* op = out + (((static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + xo) * p.c + c0) + cq * 4;
+        if (ok0) *reinterpret_cast<float4*>(op) = acc[0];
+        if (ok1) *reinterpret_cast<float4*>(op + p.c) = acc[1];
+      }
+    }
+    __syncthreads();   // the stage is free for the producer
+  }
+}
+
+// ---- host: tensor map through the driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+inline int grid1(int64_t total, int per_cta) {
+  int64_t g = (total + per_cta - 1) / per_cta;
+  return static_cast<int>(g > 0 ? g : 1);
+}
+
+}  // namespace
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_noise_bias_act_nhwc(float* out, const float* x, const float* noise, const float* noise_weight, const float* bias,
+                           const float* row_scale, float alpha, float scale, int64_t N, int C, int64_t HW, void* stream) {
+  if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "noise_bias_act_nhwc: negative size");
+  const int64_t numel = N * HW * C;
+  if (numel == 0) return GG_OK;
+  if (C % 4 != 0) return fail(GG_ERR_UNSUPPORTED, "noise_bias_act_nhwc: C must be a multiple of 4");
+  if (!out || !x) return fail(GG_ERR_BAD_ARG, "noise_bias_act_nhwc: null tensor");
+  const int64_t n_vec = numel / 4;
+  const int64_t grid = (n_vec + 4 * kT - 1) / (4 * kT);
+  if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "noise_bias_act_nhwc: tensor too large");
+  noise_bias_act_nhwc_kernel<<<static_cast<unsigned>(grid), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, x, noise, noise_weight, bias, row_scale, alpha, scale, n_vec, C / 4, HW);
+  GG_CHECK_LAUNCH("noise_bias_act_nhwc launch");
+  return GG_OK;
+}
+
+int64_t gg_nhwc_rowwise_workspace(int64_t N, int C, int64_t HW) {
+  if (N <= 0 || C <= 0 || HW <= 0) return 0;
+  const int64_t chunk = 2048;
+  return N * ((HW + chunk - 1) / chunk) * C * static_cast<int64_t>(sizeof(float));
+}
+
+static int launch_rowwise(int mode, float* out, float* dst, void* workspace, const float* x, const float* y, const float* s,
+                          float alpha, float gain, int64_t N, int C, int64_t HW, bool per_sample, void* stream) {
+  if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: negative size");
+  if (N * HW * C == 0) return GG_OK;
+  if (C % 4 != 0 || C > 1024) return fail(GG_ERR_UNSUPPORTED, "nhwc rowwise: C must be a multiple of 4 and <= 1024");
+  if (!out || !x) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: null tensor");
+  if (dst && !workspace) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: reduction needs a workspace");
+  const int c4 = C / 4;
+  const int chunk = 2048;
+  const int K = static_cast<int>((HW + chunk - 1) / chunk);
+  const int64_t grid = N * K;
+  if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: too many CTAs");
+  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;
+  const size_t smem = static_cast<size_t>(lanes_p) * C * sizeof(float);
+  float* partial = dst ? static_cast<float*>(workspace) : nullptr;
+  auto st = static_cast<cudaStream_t>(stream);
+  if (mode == 0)
+    rowwise_nhwc_kernel<0><<<static_cast<unsigned>(grid), kT, smem, st>>>(out, partial, x, dst ? y : nullptr, s, alpha, gain,
+                                                                         c4, HW, chunk, K);
+  else
+    rowwise_nhwc_kernel<1><<<static_cast<unsigned>(grid), kT, smem, st>>>(out, partial, x, y, s, alpha, gain, c4, HW, chunk, K);
+  GG_CHECK_LAUNCH("nhwc rowwise launch");
+  if (dst) {
+    const int64_t rows = per_sample ? N : 1;
+    const int kk = per_sample ? K : static_cast<int>(N * K);
+    nhwc_finish_kernel<<<static_cast<unsigned>((rows * C + 255) / 256), 256, 0, st>>>(dst, partial, rows, kk, C);
+    GG_CHECK_LAUNCH("nhwc finish launch");
+  }
+  return GG_OK;
+}
+
+int gg_channel_scale_nhwc(float* out, float* row_dot, void* workspace, const float* x, const float* y, const float* s,
+                          int64_t N, int C, int64_t HW, void* stream) {
+  if (!s) return fail(GG_ERR_BAD_ARG, "channel_scale_nhwc: null scale");
+  if (row_dot && !y) return fail(GG_ERR_BAD_ARG, "channel_scale_nhwc: row_dot needs y");
+  return launch_rowwise(0, out, row_dot, workspace, x, y, s, 0.f, 1.f, N, C, HW, true, stream);
+}
+
+int gg_bias_act_backward_nhwc(float* gx, float* grad_bias, void* workspace, const float* g, const float* out_saved,
+                              float alpha, float scale, int64_t N, int C, int64_t HW, void* stream) {
+  if (!out_saved) return fail(GG_ERR_BAD_ARG, "bias_act_backward_nhwc: null saved output");
+  return launch_rowwise(1, gx, grad_bias, workspace, g, out_saved, nullptr, alpha, scale, N, C, HW, false, stream);
+}
+
+int gg_blur_nhwc(float* out, const float* in, const float* kernel, const float* noise, const float* noise_weight,
+                 const float* bias, const float* row_scale, int64_t N, int C, int in_h, int in_w, int kernel_h,
+                 int kernel_w, int separable, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int fused, int act,
+                 float alpha, float scale, void* stream) {
+  if (N < 0 || C < 0 || in_h < 1 || in_w < 1) return fail(GG_ERR_BAD_ARG, "blur_nhwc: bad shape");
+  if (kernel_h < 1 || kernel_w < 1 || kernel_h > 4 || kernel_w > 4) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: filter must be <= 4x4");
+  if (C % kCB != 0) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: C must be a multiple of %d", kCB);
+  if (act != 1 && act != 3) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: act must be 1 or 3");
+  const int out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
+  const int out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
+  if (out_h < 1 || out_w < 1) return fail(GG_ERR_BAD_ARG, "blur_nhwc: empty output");
+  if (N == 0 || C == 0) return GG_OK;
+  if (!out || !in || !kernel) return fail(GG_ERR_BAD_ARG, "blur_nhwc: null tensor");
+  if (N > 65535) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: batch > 65535");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(GG_ERR_CUDA, "blur_nhwc: cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(in_w), static_cast<cuuint64_t>(in_h),
+                              static_cast<cuuint64_t>(N)};
+  const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(in_w) * C * 4,
+                              static_cast<cuuint64_t>(in_h) * in_w * C * 4};
+  const cuuint32_t box[4] = {kCB, kTileW, kRY, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GG_ERR_CUDA, "blur_nhwc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  BlurNhwcParams p;
+  p.n = static_cast<int>(N); p.c = C; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
+  p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.act = act; p.alpha = alpha; p.gain = scale;
+  // row segments: enough CTAs to fill the machine twice, at least 16 rows each (3 halo rows per segment)
+  const int xblocks = (out_w + kBX - 1) / kBX;
+  const int64_t base_ctas = static_cast<int64_t>(xblocks) * (C / kCB) * N;
+  int segs = static_cast<int>((2LL * 2 * sm_count() + base_ctas - 1) / base_ctas);
+  int seg_rows = (out_h + segs - 1) / segs;
+  if (seg_rows < 16) seg_rows = out_h < 16 ? out_h : 16;
+  seg_rows = (seg_rows + 3) / 4 * 4;
+  p.seg_rows = seg_rows;
+  const dim3 grid(static_cast<unsigned>(xblocks * (C / kCB)), static_cast<unsigned>((out_h + seg_rows - 1) / seg_rows),
+                  static_cast<unsigned>(N));
+  const size_t smem = static_cast<size_t>(kNS) * kStageFloats * sizeof(float);
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaSuccess;
+    const void* kernels[4] = {reinterpret_cast<const void*>(blur_nhwc_kernel<true, true>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<true, false>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<false, true>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<false, false>)};
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return cuda_fail(e, "blur_nhwc smem opt-in");
+    configured = true;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+#define GG_BLUR(F_, S_) blur_nhwc_kernel<F_, S_><<<grid, kT, smem, st>>>(out, tmap, kernel, kernel_h, kernel_w, noise, noise_weight, bias, row_scale, p)
+  if (fused) { if (separable) GG_BLUR(true, true); else GG_BLUR(true, false); }
+  else { noise = nullptr; noise_weight = nullptr; bias = nullptr; row_scale = nullptr;
+         if (separable) GG_BLUR(false, true); else GG_BLUR(false, false); }
+#undef GG_BLUR
+  GG_CHECK_LAUNCH("blur_nhwc launch");
+  return GG_OK;
+}
+
+}  // extern "C"

@@ -16,7 +16,9 @@ def fused_bias_act_raw(x, bias, ref, act, grad, alpha, scale):
     """Python face of the reference's native `fused.fused_bias_act(input, bias, refer, act, grad, alpha,
     scale)` (fused_bias_act.cpp:11-17); `None`/empty tensors mean "no bias"/"no ref"."""
     _lib.require_cuda(x, bias, ref)
-    x = x.contiguous()
+    nhwc = _lib.is_nhwc(x) and (ref is None or (ref.shape == x.shape and ref.stride() == x.stride()))
+    if not nhwc:
+        x = x.contiguous()
     if bias is not None and bias.numel() == 0:
         bias = None
     if ref is not None and ref.numel() == 0:
@@ -26,10 +28,12 @@ def fused_bias_act_raw(x, bias, ref, act, grad, alpha, scale):
     if ref is not None:
         if ref.shape != x.shape or ref.dtype != x.dtype:
             raise RuntimeError("fused_bias_act: ref must match the input's shape and dtype")
-        ref = ref.contiguous()
+        if not nhwc:
+            ref = ref.contiguous()
     step_b = 1
-    for s in x.shape[2:]:
-        step_b *= s
+    if not nhwc:  # channels-last memory is (N*H*W, C): the bias index is simply i % C
+        for s in x.shape[2:]:
+            step_b *= s
     out = torch.empty_like(x)
     rc = _lib.load().gg_fused_bias_act(out.data_ptr(), x.data_ptr(), _lib.ptr(bias), _lib.ptr(ref),
                                        _lib.dtype_code(x), act, grad, alpha, scale, x.numel(), step_b,
@@ -41,6 +45,19 @@ def fused_bias_act_raw(x, bias, ref, act, grad, alpha, scale):
 def bias_act_backward_raw(grad_output, out, alpha, scale, want_bias_grad):
     """gx = (out > 0 ? g : alpha*g)*scale and, optionally, grad_bias = gx.sum(all dims but 1) (fp32)."""
     _lib.require_cuda(grad_output, out)
+    if _lib.is_nhwc(out) and out.shape[1] % 4 == 0 and out.shape[1] <= 1024 and grad_output.shape == out.shape:
+        g = grad_output.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = out.shape
+        lib = _lib.load()
+        gx = torch.empty_like(out)
+        grad_bias = ws = None
+        if want_bias_grad:
+            grad_bias = torch.empty(c, dtype=torch.float32, device=g.device)
+            ws = torch.empty(max(1, lib.gg_nhwc_rowwise_workspace(n, c, h * w) // 4), dtype=torch.float32, device=g.device)
+        rc = lib.gg_bias_act_backward_nhwc(gx.data_ptr(), _lib.ptr(grad_bias), _lib.ptr(ws), g.data_ptr(), out.data_ptr(),
+                                           alpha, scale, n, c, h * w, _lib.stream())
+        _lib.check(rc, "gg_bias_act_backward_nhwc")
+        return gx, grad_bias
     g = grad_output.contiguous()
     out = out.contiguous()
     if g.shape != out.shape or g.dtype != out.dtype:

@@ -21,6 +21,22 @@ _cache = {}
 def channel_scale_raw(x, s, y=None):
     """out = x * s[n, c]; with `y`: also row_dot[n, c] = sum_hw x*y (fp32).  x: (N, C, H, W); s: (N, C) fp32."""
     _lib.require_cuda(x, s, y)
+    if _lib.is_nhwc(x) and x.shape[1] % 4 == 0 and x.shape[1] <= 1024:
+        n, c, h, w = x.shape
+        s = s.reshape(n * c)
+        if s.dtype != torch.float32 or not s.is_contiguous():
+            s = s.float().contiguous()
+        lib = _lib.load()
+        out = torch.empty_like(x)
+        dot = ws = None
+        if y is not None:
+            y = y.contiguous(memory_format=torch.channels_last)
+            dot = torch.empty((n, c), dtype=torch.float32, device=x.device)
+            ws = torch.empty(max(1, lib.gg_nhwc_rowwise_workspace(n, c, h * w) // 4), dtype=torch.float32, device=x.device)
+        rc = lib.gg_channel_scale_nhwc(out.data_ptr(), _lib.ptr(dot), _lib.ptr(ws), x.data_ptr(), _lib.ptr(y), s.data_ptr(),
+                                       n, c, h * w, _lib.stream())
+        _lib.check(rc, "gg_channel_scale_nhwc")
+        return out, dot
     x = x.contiguous()
     n, c = x.shape[0], x.shape[1]
     hw = x.numel() // max(n * c, 1)
@@ -108,19 +124,22 @@ def demod_coefficients(weight, style, scale, eps=1e-8):
 _wcache = {}
 
 
-def shared_conv_weight(weight, scale, transposed):
+def shared_conv_weight(weight, scale, transposed, channels_last=False):
     """scale * W as the weight of a weight-SHARED convolution: (O, I, k, k), or (I, O, k, k) for conv_transpose2d.
     Cached per (storage, version) for frozen filter banks."""
     if weight.requires_grad:
         w = weight[0] * scale
         return w.transpose(0, 1) if transposed else w
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device, float(scale), bool(transposed), weight.dtype)
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device, float(scale), bool(transposed), weight.dtype,
+           bool(channels_last))
     w = _wcache.get(key)
     if w is None:
         if len(_wcache) > 256:
             _wcache.clear()
         w = (weight.detach()[0] * scale)
         w = w.transpose(0, 1).contiguous() if transposed else w.contiguous()
+        if channels_last and w.shape[2] * w.shape[3] > 1:
+            w = w.contiguous(memory_format=torch.channels_last)
         _wcache[key] = w
     return w
 
@@ -137,9 +156,12 @@ def modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, p
         # to-RGB: a (3 x C) matrix per sample -- one batched GEMM reads the activation once, nothing is re-written
         wm = (scale * weight[0, :, :, 0, 0]).unsqueeze(0) * style.unsqueeze(1)            # (B, O, I)
         b, _, h, w_ = x.shape
+        if _lib.is_nhwc(x):   # (B, HW, I) @ (B, I, O): reads the channels-last activation in place
+            rgb = torch.bmm(x.permute(0, 2, 3, 1).reshape(b, h * w_, i), wm.type(x.dtype).transpose(1, 2))
+            return rgb.reshape(b, h, w_, o).permute(0, 3, 1, 2), None
         return torch.bmm(wm.type(x.dtype), x.reshape(b, i, h * w_)).reshape(b, o, h, w_), None
     xs = channel_scale(x, style)
-    w = shared_conv_weight(weight, scale, transposed=upsample)
+    w = shared_conv_weight(weight, scale, transposed=upsample, channels_last=_lib.is_nhwc(x))
     if upsample:
         raw = conv2d_gradfix.conv_transpose2d(xs, w.type(x.dtype), padding=0, stride=2)
     else:

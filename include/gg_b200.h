@@ -224,6 +224,30 @@ GG_API int gg_modconv_demod(float* demod, const float* wsq, const float* style, 
 GG_API int gg_modconv_modulate(float* out, const float* weight, const float* style, const float* demod,
                                float scale, int B, int O, int I, int kk, int transposed, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Channels-last (N, H, W, C; fp32; C % 4 == 0) variants of the StyledConv tail family.  Same math and reference
+ * citations as gg_noise_bias_act / gg_bias_act_backward / gg_channel_scale / gg_blur_noise_bias_act; they exist so
+ * the generator's activations can stay NHWC between cuDNN's (NHWC-native) tensor-core convolutions.
+ *   gg_blur_nhwc: upfirdn2d(up = down = 1, filter <= 4x4) on (N, H, W, C), C % 32 == 0, input rows streamed with 4-D
+ *     TMA tensor-map loads whose out-of-bounds zero fill is the padding; `separable` != 0 asserts a rank-1 filter
+ *     (two 4-tap passes; the caller tests this once per filter); `fused` != 0 adds the tail
+ *     lrelu(row_scale[n,c]*t + noise_weight*noise[n,y,x] + bias[c], alpha)*scale.
+ *   workspaces: gg_nhwc_rowwise_workspace(N, C, HW) bytes for the optional reductions (row_dot (N, C); grad_bias (C)).
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int gg_noise_bias_act_nhwc(float* out, const float* x, const float* noise, const float* noise_weight,
+                                  const float* bias, const float* row_scale, float alpha, float scale, int64_t N,
+                                  int C, int64_t HW, void* stream);
+GG_API int64_t gg_nhwc_rowwise_workspace(int64_t N, int C, int64_t HW);
+GG_API int gg_channel_scale_nhwc(float* out, float* row_dot, void* workspace, const float* x, const float* y,
+                                 const float* s, int64_t N, int C, int64_t HW, void* stream);
+GG_API int gg_bias_act_backward_nhwc(float* gx, float* grad_bias, void* workspace, const float* g,
+                                     const float* out_saved, float alpha, float scale, int64_t N, int C, int64_t HW,
+                                     void* stream);
+GG_API int gg_blur_nhwc(float* out, const float* in, const float* kernel, const float* noise,
+                        const float* noise_weight, const float* bias, const float* row_scale, int64_t N, int C,
+                        int in_h, int in_w, int kernel_h, int kernel_w, int separable, int pad_x0, int pad_x1,
+                        int pad_y0, int pad_y1, int fused, int act, float alpha, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -261,7 +261,53 @@ def gen_networks(ref_models):
     _save("networks", **out)
 
 
-EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks]
+def _mse(a, b):
+    return (a - b).pow(2).mean(dim=(1, 2, 3))
+
+
+def gen_losses(ref_models):
+    """End-to-end pin of the CALLERS of the hot path: the reference's gangealing_loss (config 2 shape, shrunk) and
+    gangealing_cluster_loss (config 5: K heads, flips, sample_from_full_res) on CPU with seeded weights; the RNG is the
+    global CPU generator, consumed in the same order by this repo's mirror."""
+    from oracle import opset
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from models.stylegan2.networks import Generator
+    from models.spatial_transformers.spatial_transformer import get_stn
+    from models.spatial_transformers.antialiased_sampling import BilinearDownsample
+    from models.latent_learner import DirectionInterpolator
+    from models.losses.loss import gangealing_loss, gangealing_cluster_loss, total_variation_loss
+    out = {}
+    for tag, heads, flips, full_res in (("uni", 1, False, False), ("cluster", 2, True, True)):
+        gen_size = 128 if full_res else 64
+        # DirectionInterpolator's random buffers are hard-coded 512-d (latent_learner.py:39-40): 512-d latent
+        g = opset.fill_parameters(Generator(gen_size, 512, 2, channel_multiplier=1).eval(), 11)
+        for prm in g.parameters():
+            prm.requires_grad = False
+        stn = get_stn(["similarity", "flow"], flow_size=64, supersize=gen_size, channel_multiplier=0.25, num_heads=heads)
+        opset.fill_parameters(stn, 12, gain=0.2)
+        ll = DirectionInterpolator(None, 2, 3, g.n_latent, num_heads=heads)
+        opset.fill_parameters(ll, 13, gain=0.5)
+        resize = BilinearDownsample(2, 3) if full_res else torch.nn.Sequential()
+        torch.manual_seed(1234)
+        if heads == 1:
+            loss, delta = gangealing_loss(g, stn, ll, _mse, resize, 0.6, 2, 512, False, "cpu", sample_from_full_res=full_res,
+                                          padding_mode="reflection")
+        else:
+            loss, delta = gangealing_cluster_loss(g, stn, ll, _mse, resize, 0.6, 2, 512, False, heads, flips, "cpu",
+                                                  sample_from_full_res=full_res, padding_mode="reflection")
+        tv = total_variation_loss(delta)
+        names = [n for n, _ in stn.named_parameters()]
+        grads = torch.autograd.grad(loss + 10.0 * tv, list(stn.parameters()) + [ll.coefficients], allow_unused=True)
+        out[tag + ".loss"], out[tag + ".tv"], out[tag + ".delta"] = loss.detach(), tv.detach(), delta.detach()
+        picked = 0
+        for n, gr in zip(names + ["ll.coefficients"], grads):
+            if gr is not None and gr.abs().max() > 0 and picked < 6 and (gr.numel() < 5000 or n == "ll.coefficients"):
+                out[tag + ".grad." + n] = gr
+                picked += 1
+    _save("losses", **out)
+
+
+EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses]
 
 if __name__ == "__main__":
     main()

@@ -117,3 +117,48 @@ def test_train_step_gradients_match_cpu_oracle():
         assert checked > 20
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_config4_point_transfer_and_splat_vs_cpu_oracle():
+    """BASELINE config 4, shrunk: flow STN at a higher output resolution -> uncongeal_points -> splat_points
+    (applications/propagate_to_images.py:44-78), GPU op set vs the same host code on the CPU oracle."""
+    from gangealing_b200.splat2d import splat2d
+    from gangealing_b200.stn import get_stn
+    from oracle import splat as SP
+    kw = dict(flow_size=64, supersize=128, channel_multiplier=0.25, num_heads=1)
+    s_cpu = get_stn(["similarity", "flow"], ops=opset.cpu_ops(), **kw).eval()
+    opset.fill_parameters(s_cpu, 21, gain=0.2)
+    s_gpu = get_stn(["similarity", "flow"], **kw).eval()
+    s_gpu.load_state_dict(s_cpu.state_dict())
+    s_gpu.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    imgs = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1)
+    ys, xs = torch.meshgrid(torch.arange(64.), torch.arange(64.), indexing="ij")
+    disc = ((ys - 32) ** 2 + (xs - 32) ** 2) < (0.35 * 64) ** 2
+    pts = torch.stack([xs[disc], ys[disc]], dim=1)[None].repeat(2, 1, 1)          # congealed-frame pixel coordinates
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            pc = s_cpu.uncongeal_points(imgs, pts, normalize_input_points=True, output_resolution=128, padding_mode="border")
+            pg = s_gpu.uncongeal_points(imgs.to(DEV), pts.to(DEV), normalize_input_points=True, output_resolution=128,
+                                        padding_mode="border")
+        assert_close(pg, pc, atol=2e-2, what="transferred points (pixels)")
+        colors = torch.randn(2, pts.shape[1], 3, generator=g)
+        expect = SP.splat_points_ref(imgs, pc, 1.3, 0.75, colors)
+        got = SP.splat_points_ref(imgs.to(DEV), pg, 1.3, 0.75, colors.to(DEV), splat_fn=splat2d)
+        assert_close(got, expect, rtol=5e-3, what="propagated image")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_cluster_config5_step_runs_on_gpu():
+    """BASELINE config 5 shape (K heads, flips, sample_from_full_res, reflection padding), shrunk: one optimisation step."""
+    from gangealing_b200.training import TrainConfig, Trainer
+    cfg = TrainConfig(gen_size=128, flow_size=64, dim_latent=64, n_mlp=2, batch=2, inject=3, num_heads=2, flips=True,
+                      ndirs=2, sample_from_full_res=True, padding_mode="reflection", gen_channel_multiplier=1,
+                      stn_channel_multiplier=0.25)
+    tr = Trainer(cfg, DEV)
+    out1 = tr.step()
+    out2 = tr.step()
+    assert all(torch.isfinite(v) for v in out2.values()) and float(out2["p"]) > 0
