@@ -44,6 +44,9 @@ SIGNATURES = {
     "gg_channel_scale_nhwc": (_I, [_P] * 6 + [_L, _I, _L, _P]),
     "gg_bias_act_backward_nhwc": (_I, [_P] * 5 + [_F, _F, _L, _I, _L, _P]),
     "gg_blur_nhwc": (_I, [_P] * 7 + [_L] + [_I] * 12 + [_F, _F, _P]),
+    "gg_to_rgb_nhwc_workspace": (_L, [_L, _I, _L]),
+    "gg_to_rgb_nhwc_forward": (_I, [_P] * 5 + [_L, _I, _L, _P]),
+    "gg_to_rgb_nhwc_backward": (_I, [_P] * 6 + [_L, _I, _L, _P]),
     "gg_splat2d_workspace": (_L, [_L, _I, _I, _I]),
     "gg_splat2d_forward": (_I, [_P] * 6 + [_L, _L, _I, _I, _I, _I, _P]),
     "gg_flow_compose_forward": (_I, [_P] * 7 + [_L, _I, _I, _I, _P]),
@@ -109,13 +112,23 @@ def is_nhwc(t):
             and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous())
 
 
-_sep_cache = {}
+def tensor_cache(t):
+    """Per-tensor-object memo, invalidated when the tensor is modified in place.  (Keyed on the Python object, not on
+    data_ptr: a freed temporary's address can be handed to a different tensor.)"""
+    ent = getattr(t, "_gg_cache", None)
+    if ent is None or ent[0] != t._version:
+        ent = (t._version, {})
+        try:
+            t._gg_cache = ent
+        except Exception:
+            pass
+    return ent[1]
 
 
 def filter_is_separable(kernel):
-    """Rank-1 test of a (<=4x4) FIR filter, cached per (storage, version): one host read per distinct filter."""
-    key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
-    v = _sep_cache.get(key)
+    """Rank-1 test of a (<=4x4) FIR filter, memoised on the tensor object: one host read per distinct filter."""
+    memo = tensor_cache(kernel)
+    v = memo.get("separable")
     if v is None:
         k = kernel.detach().float().cpu()
         big = k.abs().max()
@@ -124,10 +137,23 @@ def filter_is_separable(kernel):
         else:
             i0, j0 = divmod(int(k.abs().argmax()), k.shape[1])
             v = bool((k - torch.outer(k[:, j0], k[i0, :]) / k[i0, j0]).abs().max() <= 1e-6 * big)
-        if len(_sep_cache) > 64:
-            _sep_cache.clear()
-        _sep_cache[key] = v
+        memo["separable"] = v
     return v
+
+
+def flipped_filter(kernel):
+    """flip(kernel, [0, 1]) (the adjoint resampler's taps), memoised on the filter object so that repeated backward
+    passes neither re-launch the flip nor re-test separability (a host read: illegal during graph capture)."""
+    memo = tensor_cache(kernel)
+    f = memo.get("flipped")
+    if f is None:
+        f = torch.flip(kernel.detach(), [0, 1])
+        fm = tensor_cache(f)
+        fm["flipped"] = kernel.detach()
+        if "separable" in memo:
+            fm["separable"] = memo["separable"]
+        memo["flipped"] = f
+    return f
 
 
 def stream():

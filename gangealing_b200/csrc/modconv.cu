@@ -34,7 +34,7 @@ wsq_kernel(float* __restrict__ wsq, const float* __restrict__ w, int64_t oi, int
 // D[o, b] = sum_i Wsq[o, i] * s2[b, i]: M = 128 rows of O per CTA, N = B padded to 16.., K = I in blocks of 32 fp32
 // (= one 128-byte swizzle atom).  A and B are K-major in shared memory, SWIZZLE_128B canonical layout:
 // row r, 16-byte chunk c  ->  byte offset r*128 + ((c ^ (r & 7)) << 4); 8-row groups are 1024 B apart (SBO).
-constexpr int kDemodThreads = 128;
+constexpr int kDemodThreads = 256;   // 2 threads per A row while staging; warps 0-3 read the accumulator
 constexpr int kBlockK = 32;      // fp32 elements per k-block (128 B)
 constexpr int kUmmaK = 8;        // tf32: 32 B per MMA
 
@@ -140,17 +140,19 @@ demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, cons
 
   const uint32_t idesc = make_idesc_tf32(128, n_pad);
   const bool vec_ok = (I % 4 == 0) && ((reinterpret_cast<uintptr_t>(wsq) & 15) == 0);
-  const int o_row = o0 + tid;
+  const int a_r = tid & 127;            // A-tile row staged by this thread
+  const int a_c0 = (tid >> 7) * 4;      // ... and its first of 4 chunks (two threads share a row)
+  const int o_row = o0 + a_r;
   const float* a_row = wsq + static_cast<int64_t>(min(o_row, O - 1)) * I;
 
-  // register staging of this thread's A row: NA atoms x 8 chunks of 4 floats
-  float4 ra[NA][8];
+  // register staging of this thread's half A row: NA atoms x 4 chunks of 4 floats
+  float4 ra[NA][4];
   auto load_a = [&](int kb0) {
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int i = (kb0 + a) * kBlockK + c * 4;
+      for (int c = 0; c < 4; ++c) {
+        const int i = (kb0 + a) * kBlockK + (a_c0 + c) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (o_row < O) {
           if (vec_ok && i + 3 < I) {
@@ -175,13 +177,13 @@ demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, cons
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const float v[4] = {ra[a][c].x, ra[a][c].y, ra[a][c].z, ra[a][c].w};
         float hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) split_tf32(v[j], hi[j], lo[j]);
-        st_tile_chunk(a_hi(a), tid, c, make_float4(hi[0], hi[1], hi[2], hi[3]));
-        st_tile_chunk(a_lo(a), tid, c, make_float4(lo[0], lo[1], lo[2], lo[3]));
+        st_tile_chunk(a_hi(a), a_r, a_c0 + c, make_float4(hi[0], hi[1], hi[2], hi[3]));
+        st_tile_chunk(a_lo(a), a_r, a_c0 + c, make_float4(lo[0], lo[1], lo[2], lo[3]));
       }
       for (int rc = tid; rc < n_pad * 8; rc += kDemodThreads) {   // (row, chunk) pairs: coalesced over chunks
         const int r = rc >> 3, c = rc & 7;
@@ -227,9 +229,9 @@ demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncthreads();
 
-  // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows o0 + 32w + lane; 8 columns (batch entries) per load
+  // ---- epilogue: warp w (< 4) owns TMEM lanes [32w, 32w+32) = rows o0 + 32w + lane; 8 columns (batch entries) per load
   const int o = o0 + warp * 32 + lane;
-  for (int n0 = 0; n0 < n_pad; n0 += 8) {
+  for (int n0 = 0; n0 < (warp < 4 ? n_pad : 0); n0 += 8) {
     uint32_t v[8];
     const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(n0);
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -315,18 +317,23 @@ int gg_modconv_demod(float* demod, const float* wsq, const float* style, float s
   const int n_pad = (B + 15) / 16 * 16;
   int tmem_cols = 32;
   while (tmem_cols < n_pad) tmem_cols <<= 1;
-  const int na = (n_pad <= 64 && I > kBlockK) ? 2 : 1;
+  const int na = (n_pad <= 32 && I >= 4 * kBlockK) ? 4 : ((n_pad <= 64 && I > kBlockK) ? 2 : 1);
   const size_t smem = static_cast<size_t>(na) * (2 * 128 + 2 * n_pad) * kBlockK * sizeof(float) + 1024;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(demod_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(demod_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(demod_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "modconv_demod smem opt-in");
     configured = true;
   }
   auto st = static_cast<cudaStream_t>(stream);
-  if (na == 2)
+  if (na == 4)
+    demod_umma_kernel<4><<<(O + 127) / 128, kDemodThreads, smem, st>>>(demod, wsq, style, scale * scale, eps, B, O, I,
+                                                                      n_pad, tmem_cols);
+  else if (na == 2)
     demod_umma_kernel<2><<<(O + 127) / 128, kDemodThreads, smem, st>>>(demod, wsq, style, scale * scale, eps, B, O, I,
                                                                       n_pad, tmem_cols);
   else

@@ -71,38 +71,55 @@ rowwise_nhwc_kernel(float* __restrict__ out, float* __restrict__ partial, const 
   const int ck = blockIdx.x - n * chunks_per_sample;
   const int64_t p0 = static_cast<int64_t>(ck) * chunk, p1 = min(p0 + chunk, hw);
   const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;       // pixel lanes when C/4 <= 256
-  float4 acc[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   // a thread owns channel quads cq = tid % c4 (+ k*kT when c4 > kT is not supported: C <= 1024)
   const int cq = threadIdx.x % c4;
   const int pl = threadIdx.x / c4;
   if (pl < lanes_p) {
     float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
     if (MODE == 0) sv = __ldg(reinterpret_cast<const float4*>(s + n * c4 * 4) + cq);
-    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
-      const int64_t off = ((n * hw + p) * c4 + cq) * 4;
-      const float4 xv = *reinterpret_cast<const float4*>(x + off);
+    auto body = [&](const float4 xv, const float4 yv, int64_t off) {
       float4 o;
       if (MODE == 0) {
         o = make_float4(xv.x * sv.x, xv.y * sv.y, xv.z * sv.z, xv.w * sv.w);
         if (y) {
-          const float4 yv = *reinterpret_cast<const float4*>(y + off);
-          acc[0].x = fmaf(xv.x, yv.x, acc[0].x); acc[0].y = fmaf(xv.y, yv.y, acc[0].y);
-          acc[0].z = fmaf(xv.z, yv.z, acc[0].z); acc[0].w = fmaf(xv.w, yv.w, acc[0].w);
+          acc.x = fmaf(xv.x, yv.x, acc.x); acc.y = fmaf(xv.y, yv.y, acc.y);
+          acc.z = fmaf(xv.z, yv.z, acc.z); acc.w = fmaf(xv.w, yv.w, acc.w);
         }
-      } else {
-        const float4 rv = *reinterpret_cast<const float4*>(y + off);   // y = saved forward output
-        o.x = (rv.x > 0.f ? xv.x : xv.x * alpha) * gain; o.y = (rv.y > 0.f ? xv.y : xv.y * alpha) * gain;
-        o.z = (rv.z > 0.f ? xv.z : xv.z * alpha) * gain; o.w = (rv.w > 0.f ? xv.w : xv.w * alpha) * gain;
-        acc[0].x += o.x; acc[0].y += o.y; acc[0].z += o.z; acc[0].w += o.w;
+      } else {                                 // y = saved forward output
+        o.x = (yv.x > 0.f ? xv.x : xv.x * alpha) * gain; o.y = (yv.y > 0.f ? xv.y : xv.y * alpha) * gain;
+        o.z = (yv.z > 0.f ? xv.z : xv.z * alpha) * gain; o.w = (yv.w > 0.f ? xv.w : xv.w * alpha) * gain;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
       }
       *reinterpret_cast<float4*>(out + off) = o;
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_y = (MODE == 1) || y != nullptr;
+    int64_t p = p0 + pl;
+    // 4 pixels per trip: all loads issued before the first dependent store (memory-level parallelism)
+    for (; p + 3 * lanes_p < p1; p += 4 * lanes_p) {
+      float4 xv[4], yv[4];
+      int64_t off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        off[u] = ((n * hw + p + u * lanes_p) * c4 + cq) * 4;
+        xv[u] = __ldcs(reinterpret_cast<const float4*>(x + off[u]));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) yv[u] = has_y ? __ldcs(reinterpret_cast<const float4*>(y + off[u])) : zero;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(xv[u], yv[u], off[u]);
+    }
+    for (; p < p1; p += lanes_p) {
+      const int64_t off = ((n * hw + p) * c4 + cq) * 4;
+      const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + off));
+      const float4 yv = has_y ? __ldcs(reinterpret_cast<const float4*>(y + off)) : zero;
+      body(xv, yv, off);
     }
   }
   if (partial) {
     float4* r4 = reinterpret_cast<float4*>(red);
-    if (pl < lanes_p) r4[pl * c4 + cq] = acc[0];
+    if (pl < lanes_p) r4[pl * c4 + cq] = acc;
     __syncthreads();
     if (threadIdx.x < c4) {
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -124,6 +141,140 @@ __global__ void nhwc_finish_kernel(float* __restrict__ dst, const float* __restr
   float acc = 0.f;
   for (int k = 0; k < K; ++k) acc += partial[(r * K + k) * C + c];
   dst[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ to-RGB (1x1, 3 outputs)
+// out[n,o,p] = sum_i wm[n,o,i] * x[n,p,i] + bias[o] + skip[n,o,p]   x: NHWC, out/skip: planar (N, 3, HW)
+// One pass over x (the only large operand).  A group of 8 lanes owns 4 consecutive pixels: every lane streams its
+// channel quads (l + 8j) of the 4 pixels (4 independent 128-bit loads per trip), the 3 x C modulated filter sits in
+// shared memory, and the 12 partial dot products are combined with 3 butterfly steps.
+__global__ void __launch_bounds__(kT)
+to_rgb_nhwc_fwd_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ wm,
+                       const float* __restrict__ bias, const float* __restrict__ skip, int c4, int64_t hw, int chunk,
+                       int chunks_per_sample) {
+  extern __shared__ __align__(16) float wsm[];          // [3][C]
+  const int64_t n = blockIdx.x / chunks_per_sample;
+  const int ck = blockIdx.x - n * chunks_per_sample;
+  const int64_t p0 = static_cast<int64_t>(ck) * chunk, p1 = min(p0 + chunk, hw);
+  {
+    const float4* src = reinterpret_cast<const float4*>(wm + n * 3 * c4 * 4);
+    float4* dst = reinterpret_cast<float4*>(wsm);
+    for (int i = threadIdx.x; i < 3 * c4; i += kT) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const float4* w4 = reinterpret_cast<const float4*>(wsm);
+  const int l = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const bool vec_ok = (hw & 3) == 0;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);     // groups of one warp may leave the loop at different trips
+  for (int64_t pb = p0 + grp * 4; pb < p1; pb += (kT / 8) * 4) {
+    float acc[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = acc[u][2] = 0.f;
+    const float4* xp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t pu = min(pb + u, p1 - 1);             // clamped: a tail pixel is recomputed, never stored
+      xp[u] = reinterpret_cast<const float4*>(x + (n * hw + pu) * c4 * 4);
+    }
+    for (int q = l; q < c4; q += 8) {
+      float4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = __ldcs(xp[u] + q);
+      const float4 w0 = w4[q], w1 = w4[c4 + q], w2 = w4[2 * c4 + q];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u][0] = fmaf(xv[u].x, w0.x, fmaf(xv[u].y, w0.y, fmaf(xv[u].z, w0.z, fmaf(xv[u].w, w0.w, acc[u][0]))));
+        acc[u][1] = fmaf(xv[u].x, w1.x, fmaf(xv[u].y, w1.y, fmaf(xv[u].z, w1.z, fmaf(xv[u].w, w1.w, acc[u][1]))));
+        acc[u][2] = fmaf(xv[u].x, w2.x, fmaf(xv[u].y, w2.y, fmaf(xv[u].z, w2.z, fmaf(xv[u].w, w2.w, acc[u][2]))));
+      }
+    }
+#pragma unroll
+    for (int m = 4; m >= 1; m >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) acc[u][o] += __shfl_xor_sync(gmask, acc[u][o], m);
+    if (l < 3) {                                           // lane o of the group stores output plane o
+      const int o = l;
+      float r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = (o == 0 ? acc[u][0] : o == 1 ? acc[u][1] : acc[u][2]) + (bias ? __ldg(bias + o) : 0.f);
+      const int64_t off = (n * 3 + o) * hw + pb;
+      if (vec_ok && pb + 3 < p1) {
+        if (skip) {
+          const float4 sk = __ldg(reinterpret_cast<const float4*>(skip + off));
+          r[0] += sk.x; r[1] += sk.y; r[2] += sk.z; r[3] += sk.w;
+        }
+        *reinterpret_cast<float4*>(out + off) = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (pb + u < p1) out[off + u] = r[u] + (skip ? __ldg(skip + off + u) : 0.f);
+      }
+    }
+  }
+}
+
+// Backward: gx[n,p,i] = sum_o wm[n,o,i] g[n,o,p]  and  gwm[n,o,i] = sum_p g[n,o,p] x[n,p,i], one pass over x / gx.
+// Thread = (channel quad, pixel lane) as in rowwise_nhwc_kernel; the three g planes are warp-broadcast loads.
+__global__ void __launch_bounds__(kT)
+to_rgb_nhwc_bwd_kernel(float* __restrict__ gx, float* __restrict__ partial, const float* __restrict__ g,
+                       const float* __restrict__ x, const float* __restrict__ wm, int c4, int64_t hw, int chunk,
+                       int chunks_per_sample) {
+  extern __shared__ float red[];                          // [pixel lanes][3][C]
+  const int64_t n = blockIdx.x / chunks_per_sample;
+  const int ck = blockIdx.x - n * chunks_per_sample;
+  const int64_t p0 = static_cast<int64_t>(ck) * chunk, p1 = min(p0 + chunk, hw);
+  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;
+  const int cq = threadIdx.x % c4, pl = threadIdx.x / c4;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+  if (pl < lanes_p) {
+    const float4* wp = reinterpret_cast<const float4*>(wm + n * 3 * c4 * 4);
+    const float4 w0 = __ldg(wp + cq), w1 = __ldg(wp + c4 + cq), w2 = __ldg(wp + 2 * c4 + cq);
+    const float* g0 = g + n * 3 * hw;
+    auto body = [&](int64_t p, const float4 xv, float s0, float s1, float s2) {
+      float4 o;
+      o.x = fmaf(w2.x, s2, fmaf(w1.x, s1, w0.x * s0)); o.y = fmaf(w2.y, s2, fmaf(w1.y, s1, w0.y * s0));
+      o.z = fmaf(w2.z, s2, fmaf(w1.z, s1, w0.z * s0)); o.w = fmaf(w2.w, s2, fmaf(w1.w, s1, w0.w * s0));
+      if (gx) *reinterpret_cast<float4*>(gx + ((n * hw + p) * c4 + cq) * 4) = o;
+      a0.x = fmaf(s0, xv.x, a0.x); a0.y = fmaf(s0, xv.y, a0.y); a0.z = fmaf(s0, xv.z, a0.z); a0.w = fmaf(s0, xv.w, a0.w);
+      a1.x = fmaf(s1, xv.x, a1.x); a1.y = fmaf(s1, xv.y, a1.y); a1.z = fmaf(s1, xv.z, a1.z); a1.w = fmaf(s1, xv.w, a1.w);
+      a2.x = fmaf(s2, xv.x, a2.x); a2.y = fmaf(s2, xv.y, a2.y); a2.z = fmaf(s2, xv.z, a2.z); a2.w = fmaf(s2, xv.w, a2.w);
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t p = p0 + pl;
+    for (; p + 3 * lanes_p < p1; p += 4 * lanes_p) {
+      float4 xv[4];
+      float s[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t pu = p + u * lanes_p;
+        xv[u] = partial ? __ldcs(reinterpret_cast<const float4*>(x + ((n * hw + pu) * c4 + cq) * 4)) : zero;
+        s[u][0] = __ldg(g0 + pu); s[u][1] = __ldg(g0 + hw + pu); s[u][2] = __ldg(g0 + 2 * hw + pu);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(p + u * lanes_p, xv[u], s[u][0], s[u][1], s[u][2]);
+    }
+    for (; p < p1; p += lanes_p) {
+      const float4 xv = partial ? __ldcs(reinterpret_cast<const float4*>(x + ((n * hw + p) * c4 + cq) * 4)) : zero;
+      body(p, xv, __ldg(g0 + p), __ldg(g0 + hw + p), __ldg(g0 + 2 * hw + p));
+    }
+  }
+  if (partial) {
+    float4* r4 = reinterpret_cast<float4*>(red);
+    if (pl < lanes_p) {
+      r4[(pl * 3 + 0) * c4 + cq] = a0; r4[(pl * 3 + 1) * c4 + cq] = a1; r4[(pl * 3 + 2) * c4 + cq] = a2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * c4; i += kT) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < lanes_p; ++q) {
+        const float4 v = r4[q * 3 * c4 + i];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      reinterpret_cast<float4*>(partial + static_cast<int64_t>(blockIdx.x) * 3 * c4 * 4)[i] = t;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ blur (TMA tiled)
@@ -377,9 +528,21 @@ int gg_noise_bias_act_nhwc(float* out, const float* x, const float* noise, const
   return GG_OK;
 }
 
+// Pixels per CTA: enough CTAs to fill the machine ~8x over, at least 4 trips of the CTA's pixel lanes each.
+static int64_t rowwise_chunk(int64_t N, int C, int64_t HW) {
+  const int c4 = C / 4;
+  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;
+  const int64_t target = 8LL * sm_count();
+  int64_t k = (target + N - 1) / N;
+  const int64_t kmax = (HW + 4 * lanes_p - 1) / (4 * lanes_p);
+  if (k > kmax) k = kmax;
+  if (k < 1) k = 1;
+  return (HW + k - 1) / k;
+}
+
 int64_t gg_nhwc_rowwise_workspace(int64_t N, int C, int64_t HW) {
-  if (N <= 0 || C <= 0 || HW <= 0) return 0;
-  const int64_t chunk = 2048;
+  if (N <= 0 || C <= 0 || HW <= 0 || C % 4 != 0) return 0;
+  const int64_t chunk = rowwise_chunk(N, C, HW);
   return N * ((HW + chunk - 1) / chunk) * C * static_cast<int64_t>(sizeof(float));
 }
 
@@ -391,7 +554,9 @@ static int launch_rowwise(int mode, float* out, float* dst, void* workspace, con
   if (!out || !x) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: null tensor");
   if (dst && !workspace) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: reduction needs a workspace");
   const int c4 = C / 4;
-  const int chunk = 2048;
+  const int64_t chunk64 = rowwise_chunk(N, C, HW);
+  if (chunk64 > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: plane too large");
+  const int chunk = static_cast<int>(chunk64);
   const int K = static_cast<int>((HW + chunk - 1) / chunk);
   const int64_t grid = N * K;
   if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: too many CTAs");
@@ -425,6 +590,58 @@ int gg_bias_act_backward_nhwc(float* gx, float* grad_bias, void* workspace, cons
                               float alpha, float scale, int64_t N, int C, int64_t HW, void* stream) {
   if (!out_saved) return fail(GG_ERR_BAD_ARG, "bias_act_backward_nhwc: null saved output");
   return launch_rowwise(1, gx, grad_bias, workspace, g, out_saved, nullptr, alpha, scale, N, C, HW, false, stream);
+}
+
+int64_t gg_to_rgb_nhwc_workspace(int64_t N, int C, int64_t HW) { return 3 * gg_nhwc_rowwise_workspace(N, C, HW); }
+
+int gg_to_rgb_nhwc_forward(float* out, const float* x, const float* wm, const float* bias, const float* skip, int64_t N,
+                           int C, int64_t HW, void* stream) {
+  if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc: negative size");
+  if (N * HW == 0) return GG_OK;
+  if (C < 32 || C % 32 != 0 || C > 1024) return fail(GG_ERR_UNSUPPORTED, "to_rgb_nhwc: C must be a multiple of 32, <= 1024");
+  if (!out || !x || !wm) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc: null tensor");
+  // pixels per CTA: a multiple of the 128 pixels one trip covers, ~8 CTAs per SM over the whole batch
+  const int64_t target = 8LL * sm_count();
+  int64_t k = (target + N - 1) / N;
+  const int64_t kmax = (HW + 127) / 128;
+  if (k > kmax) k = kmax;
+  if (k < 1) k = 1;
+  int64_t chunk = ((HW + k - 1) / k + 127) / 128 * 128;
+  if (chunk > 0x7fffff00LL) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc: plane too large");
+  const int K = static_cast<int>((HW + chunk - 1) / chunk);
+  const int64_t grid = N * K;
+  if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc: too many CTAs");
+  to_rgb_nhwc_fwd_kernel<<<static_cast<unsigned>(grid), kT, static_cast<size_t>(3) * C * sizeof(float),
+                           static_cast<cudaStream_t>(stream)>>>(out, x, wm, bias, skip, C / 4, HW, static_cast<int>(chunk), K);
+  GG_CHECK_LAUNCH("to_rgb_nhwc forward launch");
+  return GG_OK;
+}
+
+int gg_to_rgb_nhwc_backward(float* gx, float* gwm, void* workspace, const float* g, const float* x, const float* wm,
+                            int64_t N, int C, int64_t HW, void* stream) {
+  if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: negative size");
+  if (N * HW == 0 || C == 0) return GG_OK;
+  if (C % 4 != 0 || C > 1024) return fail(GG_ERR_UNSUPPORTED, "to_rgb_nhwc backward: C must be a multiple of 4, <= 1024");
+  if (!g || !wm || (!gx && !gwm)) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: null tensor");
+  if (gwm && (!x || !workspace)) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: gwm needs x and a workspace");
+  const int c4 = C / 4;
+  const int64_t chunk64 = rowwise_chunk(N, C, HW);
+  if (chunk64 > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: plane too large");
+  const int chunk = static_cast<int>(chunk64);
+  const int K = static_cast<int>((HW + chunk - 1) / chunk);
+  const int64_t grid = N * K;
+  if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: too many CTAs");
+  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;
+  const size_t smem = static_cast<size_t>(lanes_p) * 3 * C * sizeof(float);
+  auto st = static_cast<cudaStream_t>(stream);
+  float* partial = gwm ? static_cast<float*>(workspace) : nullptr;
+  to_rgb_nhwc_bwd_kernel<<<static_cast<unsigned>(grid), kT, smem, st>>>(gx, partial, g, x, wm, c4, HW, chunk, K);
+  GG_CHECK_LAUNCH("to_rgb_nhwc backward launch");
+  if (gwm) {
+    nhwc_finish_kernel<<<static_cast<unsigned>((N * 3 * C + 255) / 256), 256, 0, st>>>(gwm, partial, N, K, 3 * C);
+    GG_CHECK_LAUNCH("to_rgb_nhwc finish launch");
+  }
+  return GG_OK;
 }
 
 int gg_blur_nhwc(float* out, const float* in, const float* kernel, const float* noise, const float* noise_weight,

@@ -15,9 +15,6 @@ from torch.autograd.function import once_differentiable
 
 from .. import _lib
 
-_cache = {}
-
-
 def channel_scale_raw(x, s, y=None):
     """out = x * s[n, c]; with `y`: also row_dot[n, c] = sum_hw x*y (fp32).  x: (N, C, H, W); s: (N, C) fp32."""
     _lib.require_cuda(x, s, y)
@@ -84,13 +81,10 @@ class _Demod(Function):
     @staticmethod
     def forward(ctx, weight, style, scale, eps):
         _, o, i, kh, kw = weight.shape
-        w3 = weight.detach().reshape(o, i, kh * kw)
-        if w3.dtype != torch.float32 or not w3.is_contiguous():
-            w3 = w3.float().contiguous()
         s = style.detach()
         if s.dtype != torch.float32 or not s.is_contiguous():
             s = s.float().contiguous()
-        wsq, _ = _derived(w3, False)
+        _, wsq, _ = _derived(weight, False)
         b = s.shape[0]
         lib = _lib.load()
         demod = torch.empty((b, o), dtype=torch.float32, device=s.device)
@@ -121,45 +115,86 @@ def demod_coefficients(weight, style, scale, eps=1e-8):
     return _Demod.apply(weight, style, float(scale), float(eps))
 
 
-_wcache = {}
-
-
 def shared_conv_weight(weight, scale, transposed, channels_last=False):
     """scale * W as the weight of a weight-SHARED convolution: (O, I, k, k), or (I, O, k, k) for conv_transpose2d.
-    Cached per (storage, version) for frozen filter banks."""
+    Memoised on the parameter object for frozen filter banks."""
     if weight.requires_grad:
         w = weight[0] * scale
         return w.transpose(0, 1) if transposed else w
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device, float(scale), bool(transposed), weight.dtype,
-           bool(channels_last))
-    w = _wcache.get(key)
+    memo = _lib.tensor_cache(weight)
+    key = ("shared", float(scale), bool(transposed), bool(channels_last), weight.dtype)
+    w = memo.get(key)
     if w is None:
-        if len(_wcache) > 256:
-            _wcache.clear()
         w = (weight.detach()[0] * scale)
         w = w.transpose(0, 1).contiguous() if transposed else w.contiguous()
         if channels_last and w.shape[2] * w.shape[3] > 1:
             w = w.contiguous(memory_format=torch.channels_last)
-        _wcache[key] = w
+        memo[key] = w
     return w
 
 
-def modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, padding=1, eps=1e-8):
+class _ToRGB(Function):
+    """out = wm (B, 3, C) applied to the channels-last activation + bias + skip, one pass (csrc/nhwc.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, wm, bias, skip):
+        _lib.require_cuda(x, wm, bias, skip)
+        n, c, h, w = x.shape
+        wmc = wm.detach().float().contiguous()
+        b = bias.detach().float().reshape(-1).contiguous() if bias is not None else None
+        sk = skip.detach().float().contiguous() if skip is not None else None
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=x.device)
+        rc = _lib.load().gg_to_rgb_nhwc_forward(out.data_ptr(), x.data_ptr(), wmc.data_ptr(), _lib.ptr(b), _lib.ptr(sk),
+                                                n, c, h * w, _lib.stream())
+        _lib.check(rc, "gg_to_rgb_nhwc_forward")
+        ctx.save_for_backward(x, wmc)
+        ctx.meta = (bias.shape if bias is not None else None, wm.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, wmc = ctx.saved_tensors
+        bias_shape, wm_dtype = ctx.meta
+        need_x, need_w, need_b, need_s = ctx.needs_input_grad
+        n, c, h, w = x.shape
+        g = g.float().contiguous()
+        lib = _lib.load()
+        gx = gw = ws = None
+        if need_x:
+            gx = torch.empty_like(x)
+        if need_w:
+            gw = torch.empty((n, 3, c), dtype=torch.float32, device=x.device)
+            ws = torch.empty(max(1, lib.gg_to_rgb_nhwc_workspace(n, c, h * w) // 4), dtype=torch.float32, device=x.device)
+        if need_x or need_w:
+            rc = lib.gg_to_rgb_nhwc_backward(_lib.ptr(gx), _lib.ptr(gw), _lib.ptr(ws), g.data_ptr(), x.data_ptr(),
+                                             wmc.data_ptr(), n, c, h * w, _lib.stream())
+            _lib.check(rc, "gg_to_rgb_nhwc_backward")
+        gb = g.sum(dim=(0, 2, 3)).reshape(bias_shape) if need_b and bias_shape is not None else None
+        return gx, (gw.to(wm_dtype) if gw is not None else None), gb, (g if need_s else None)
+
+
+def modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, padding=1, eps=1e-8, bias=None, skip=None):
     """ModulatedConv2d's convolution, B200-first: conv(scale*W*s, x) == conv(scale*W, x*s), so ONE weight-shared
     (dense, tensor-core friendly) cuDNN convolution replaces the reference's grouped convolution over B materialised
     filter banks (networks.py:255-280); measured 1.3-3x faster on B200 (tools/convbench.py).
     Returns (raw, demod): the caller applies `demod` (B, O) -- or None -- as the per-(sample, channel) row scale of its
-    fused activation tail (it commutes with the blur)."""
+    fused activation tail (it commutes with the blur).  `bias` (1, O, 1, 1) / `skip` (B, O, H, W) are added to `raw`
+    (the to-RGB layer's epilogue, networks.py:400-405)."""
     from . import conv2d_gradfix
     _, o, i, kh, kw = weight.shape
     if kh == 1 and kw == 1 and not upsample and not demodulate:
-        # to-RGB: a (3 x C) matrix per sample -- one batched GEMM reads the activation once, nothing is re-written
+        # to-RGB: a (3 x C) matrix per sample
         wm = (scale * weight[0, :, :, 0, 0]).unsqueeze(0) * style.unsqueeze(1)            # (B, O, I)
         b, _, h, w_ = x.shape
+        if _lib.is_nhwc(x) and o == 3 and i % 32 == 0 and i <= 1024 and x.dtype == torch.float32:
+            return _ToRGB.apply(x, wm, bias, skip), None      # one fused pass over the channels-last activation
         if _lib.is_nhwc(x):   # (B, HW, I) @ (B, I, O): reads the channels-last activation in place
             rgb = torch.bmm(x.permute(0, 2, 3, 1).reshape(b, h * w_, i), wm.type(x.dtype).transpose(1, 2))
-            return rgb.reshape(b, h, w_, o).permute(0, 3, 1, 2), None
-        return torch.bmm(wm.type(x.dtype), x.reshape(b, i, h * w_)).reshape(b, o, h, w_), None
+            rgb = rgb.reshape(b, h, w_, o).permute(0, 3, 1, 2)
+        else:                 # one batched GEMM reads the activation once, nothing is re-written
+            rgb = torch.bmm(wm.type(x.dtype), x.reshape(b, i, h * w_)).reshape(b, o, h, w_)
+        return _epilogue(rgb, bias, skip), None
     xs = channel_scale(x, style)
     w = shared_conv_weight(weight, scale, transposed=upsample, channels_last=_lib.is_nhwc(x))
     if upsample:
@@ -167,24 +202,34 @@ def modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, p
     else:
         raw = conv2d_gradfix.conv2d(xs, w.type(x.dtype), padding=padding)
     d = demod_coefficients(weight, style, scale, eps) if demodulate else None
-    return raw, d
+    return _epilogue(raw, bias, skip), d
 
 
-def _derived(weight3, need_t):
-    """(Wsq (O, I), W^T (I, O, kk) or None) for a filter bank, cached on (data_ptr, version, shape)."""
-    key = (weight3.data_ptr(), weight3._version, tuple(weight3.shape), weight3.device)
-    ent = _cache.get(key)
+def _epilogue(raw, bias, skip):
+    if bias is not None:
+        raw = raw + bias.type(raw.dtype)
+    if skip is not None:
+        raw = raw.float() + skip
+    return raw
+
+
+def _derived(weight, need_t):
+    """(W as (O, I, kk) fp32, Wsq (O, I), W^T (I, O, kk) or None) of a filter bank, memoised on the parameter object
+    (invalidated by in-place updates)."""
+    memo = _lib.tensor_cache(weight)
+    ent = memo.get("derived")
     if ent is None:
-        if len(_cache) > 256:
-            _cache.clear()
-        o, i, kk = weight3.shape
-        wsq = torch.empty((o, i), dtype=torch.float32, device=weight3.device)
-        _lib.check(_lib.load().gg_modconv_wsq(wsq.data_ptr(), weight3.data_ptr(), o, i, kk, _lib.stream()), "gg_modconv_wsq")
-        ent = [wsq, None]
-        _cache[key] = ent
-    if need_t and ent[1] is None:
-        ent[1] = weight3.transpose(0, 1).contiguous()
-    return ent[0], ent[1]
+        _, o, i, kh, kw = weight.shape
+        w3 = weight.detach().reshape(o, i, kh * kw)
+        if w3.dtype != torch.float32 or not w3.is_contiguous():
+            w3 = w3.float().contiguous()
+        wsq = torch.empty((o, i), dtype=torch.float32, device=w3.device)
+        _lib.check(_lib.load().gg_modconv_wsq(wsq.data_ptr(), w3.data_ptr(), o, i, kh * kw, _lib.stream()), "gg_modconv_wsq")
+        ent = [w3, wsq, None]
+        memo["derived"] = ent
+    if need_t and ent[2] is None:
+        ent[2] = ent[0].transpose(0, 1).contiguous()
+    return ent[0], ent[1], ent[2]
 
 
 def modulated_weight_composite(weight, style, scale, demodulate=True, transposed=False, eps=1e-8):
@@ -206,15 +251,12 @@ class _ModulatedWeight(Function):
         _, o, i, kh, kw = weight.shape
         kk = kh * kw
         b = style.shape[0]
-        w3 = weight.detach().reshape(o, i, kk)
-        if w3.dtype != torch.float32 or not w3.is_contiguous():
-            w3 = w3.float().contiguous()
         s = style.detach()
         if s.dtype != torch.float32 or not s.is_contiguous():
             s = s.float().contiguous()
         lib = _lib.load()
         st = _lib.stream()
-        wsq, wt = _derived(w3, transposed)
+        w3, wsq, wt = _derived(weight, transposed)
         demod = None
         if demodulate:
             demod = torch.empty((b, o), dtype=torch.float32, device=s.device)

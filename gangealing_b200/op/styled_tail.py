@@ -67,7 +67,7 @@ class _StyledTail(Function):
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record()
                 rc = lib.gg_blur_nhwc(out.data_ptr(), x.data_ptr(), taps.data_ptr(), _lib.ptr(nz), _lib.ptr(nw), _lib.ptr(b),
-                                      _lib.ptr(rs), n, c, in_h, in_w, kh, kw, 1 if _lib.filter_is_separable(taps) else 0,
+                                      _lib.ptr(rs), n, c, in_h, in_w, kh, kw, 1 if _lib.filter_is_separable(kernel) else 0,
                                       pad[0], pad[1], pad[2], pad[3], 1, 3, negative_slope, scale, _lib.stream())
                 _lib.check(rc, "gg_blur_nhwc")
                 if TIMING is not None:
@@ -131,7 +131,7 @@ class _StyledTail(Function):
             else:
                 kh, kw = kernel.shape
                 gp = grad_pad(in_size[2], in_size[3], out.shape[2], out.shape[3], kh, kw, (1, 1), (1, 1), pad)
-                g_t = UpFirDn2d.apply(gx, torch.flip(kernel, [0, 1]), (1, 1), (1, 1), gp)  # adjoint blur
+                g_t = UpFirDn2d.apply(gx, _lib.flipped_filter(kernel), (1, 1), (1, 1), gp)  # adjoint blur
             if row_scale is not None:
                 # one fused pass: g_x = g_t * rs  and  g_rs = sum_hw g_t * x   (<B(x), g> = <x, B^T g>)
                 g_x, dot = channel_scale_raw(g_t, row_scale.detach().reshape(in_size[0], in_size[1]),

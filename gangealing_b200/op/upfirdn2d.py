@@ -42,7 +42,7 @@ def upfirdn2d_raw(x, kernel, up, down, pad):
         # channels-last activations stay channels-last (TMA tensor-map kernel, csrc/nhwc.cu)
         out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         rc = _lib.load().gg_blur_nhwc(out.data_ptr(), x.data_ptr(), taps.data_ptr(), None, None, None, None, n, c, in_h,
-                                      in_w, kh, kw, 1 if _lib.filter_is_separable(taps) else 0, pad[0], pad[1], pad[2],
+                                      in_w, kh, kw, 1 if _lib.filter_is_separable(kernel) else 0, pad[0], pad[1], pad[2],
                                       pad[3], 0, 1, 0.0, 1.0, _lib.stream())
         _lib.check(rc, "gg_blur_nhwc")
         return out
@@ -72,7 +72,7 @@ class _UpFirDn2dGrad(Function):
 
     @staticmethod
     def forward(ctx, grad_output, kernel, up, down, pad, g_pad, in_size):
-        flipped = torch.flip(kernel, [0, 1])
+        flipped = _lib.flipped_filter(kernel)
         grad_input = upfirdn2d_raw(grad_output, flipped, down, up, g_pad)
         if tuple(grad_input.shape[2:]) != tuple(in_size[2:]):
             raise RuntimeError("upfirdn2d backward: adjoint produced %s, expected %s" %

@@ -64,6 +64,7 @@ class SpatialTransformer(nn.Module):
         self.input_downsample_required = supersize > flow_size
         self.stn_in_size = flow_size
         self.is_flow = transform == "flow"
+        self.channels_last = False        # run the conv trunk on NHWC activations (cuDNN's native layout; CUDA only)
         channels = channel_table(channel_multiplier)
         convs = [ConvLayer(3, int(channels[flow_size]), 1, ops=ops)]
         log_size = int(math.log(flow_size, 2))
@@ -143,9 +144,11 @@ class SpatialTransformer(nn.Module):
                        pack=False):
         regression_input = self.input_downsample(input_img) if input_img.size(-1) > self.stn_in_size else input_img
         source = input_img if input_img_for_sampling is None else input_img_for_sampling
+        if self.channels_last and regression_input.is_cuda:
+            regression_input = regression_input.contiguous(memory_format=torch.channels_last)
         feat = self.final_conv(self.convs(regression_input))
         if not self.is_flow:
-            feat = self.final_linear(feat.view(feat.shape[0], -1))
+            feat = self.final_linear(feat.reshape(feat.shape[0], -1))   # logical (C, H, W) order in either layout
         res = output_resolution if output_resolution is not None else self.stn_in_size
         out, grid, M, oob = self.warp_head(source, feat, output_resolution=res, base_warp=base_warp, stop_grad=stop_grad,
                                            alpha=alpha, padding_mode=padding_mode,

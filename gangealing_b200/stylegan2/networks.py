@@ -264,9 +264,16 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
     def forward(self, input, style, skip=None):
-        out = self.conv(input, style) + self.bias.type(input.dtype)
-        if skip is not None:
-            out = out.float() + self.upsample(skip)
+        conv = self.conv
+        up = self.upsample(skip) if skip is not None else None
+        if not (conv.normalize or conv.downsample or conv.upsample or conv.demodulate):
+            # bias and skip ride in the op set's to-RGB epilogue (one pass over the activation on sm_100a)
+            out, _ = conv.ops.modulated_conv2d(input, conv.weight, conv.modulation(style), conv.scale, False, False,
+                                               conv.padding, conv.eps, bias=self.bias, skip=up)
+            return out
+        out = conv(input, style) + self.bias.type(input.dtype)
+        if up is not None:
+            out = out.float() + up
         return out
 
 
@@ -338,6 +345,9 @@ class Generator(nn.Module):
             in_channel = out_channel
         self.n_latent = self.log_size * 2 - 2
         self.num_fp16_res, self.run_fp32 = num_fp16_res, run_fp32
+        # keep the synthesis activations channels-last (NHWC) between cuDNN's NHWC-native convolutions; the fused
+        # kernels of this package have native channels-last variants (csrc/nhwc.cu).  Set by the Trainer on CUDA.
+        self.channels_last = False
 
     def make_noise(self, batch_size=1):
         device = self.input.input.device
@@ -375,7 +385,10 @@ class Generator(nn.Module):
             latent = torch.cat([styles[0].unsqueeze(1).repeat(1, inject_index, 1),
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
 
-        out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0])
+        x0 = self.input(latent)
+        if self.channels_last:
+            x0 = x0.contiguous(memory_format=torch.channels_last)
+        out = self.conv1(x0, latent[:, 0], noise=noise[0])
         skip = self.to_rgb1(out, latent[:, 1])
         i = 1
         for j, (up, conv, n_up, n_conv, to_rgb) in enumerate(

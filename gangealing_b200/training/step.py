@@ -59,6 +59,7 @@ class TrainConfig:
     freeze_ll: bool = False
     psi: float = 0.5
     seed: int = 0
+    channels_last: bool = True        # generator + STN-trunk activations NHWC on CUDA (no cuDNN layout conversions)
 
 
 class Trainer:
@@ -70,11 +71,16 @@ class Trainer:
         torch.manual_seed(cfg.seed)  # identical weights on every rank (stands in for the shared checkpoint)
         self.generator = Generator(cfg.gen_size, cfg.dim_latent, cfg.n_mlp, channel_multiplier=cfg.gen_channel_multiplier,
                                    ops=ops).to(device).eval()
+        self.generator.channels_last = torch.device(device).type == "cuda" and ops is None and cfg.channels_last
         kw = dict(flow_size=cfg.flow_size, supersize=cfg.gen_size if cfg.sample_from_full_res else cfg.flow_size,
                   channel_multiplier=cfg.stn_channel_multiplier, num_heads=cfg.num_heads, ops=ops)
         self.stn = get_stn(list(cfg.transform), **kw).to(device)
         self.t_ema = get_stn(list(cfg.transform), **kw).to(device)
         self.t_ema.load_state_dict(self.stn.state_dict())
+        if self.generator.channels_last:
+            for m in list(self.stn.modules()) + list(self.t_ema.modules()):
+                if hasattr(m, "channels_last") and hasattr(m, "stn_in_size"):
+                    m.channels_last = True
         self.ll = DirectionInterpolator(None, cfg.ndirs, cfg.inject, self.generator.n_latent, num_heads=cfg.num_heads,
                                         dim_latent=cfg.dim_latent).to(device)
         self.loss_fn = get_perceptual_loss(device, seed=cfg.seed + 1)

@@ -248,6 +248,20 @@ GG_API int gg_blur_nhwc(float* out, const float* in, const float* kernel, const 
                         int in_h, int in_w, int kernel_h, int kernel_w, int separable, int pad_x0, int pad_x1,
                         int pad_y0, int pad_y1, int fused, int act, float alpha, float scale, void* stream);
 
+/* to-RGB on channels-last activations (reference models/stylegan2/networks.py:389-405 `ToRGB.forward`: a 1x1 modulated
+ * convolution without demodulation + bias + the up-sampled skip image; the reference builds B filter banks and runs a
+ * grouped convolution).  One pass over the activation:
+ *   out[n,o,p] = sum_i wm[n,o,i] * x[n,p,i] + bias[o] + skip[n,o,p]      x: (N, HW, C) NHWC; wm: (N, 3, C) fp32
+ *   out, skip (optional), g: planar (N, 3, HW).  C % 32 == 0, C <= 1024.
+ * backward: gx[n,p,i] = sum_o wm[n,o,i] g[n,o,p]  (NULL: skipped);  gwm[n,o,i] = sum_p g[n,o,p] x[n,p,i]  (NULL: skipped;
+ * otherwise `workspace` of gg_to_rgb_nhwc_workspace(N, C, HW) bytes, deterministic two-stage reduction). */
+GG_API int64_t gg_to_rgb_nhwc_workspace(int64_t N, int C, int64_t HW);
+GG_API int gg_to_rgb_nhwc_forward(float* out, const float* x, const float* wm, const float* bias, const float* skip,
+                                  int64_t N, int C, int64_t HW, void* stream);
+GG_API int gg_to_rgb_nhwc_backward(float* gx, float* gwm, void* workspace, const float* g, const float* x,
+                                   const float* wm, int64_t N, int C, int64_t HW, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ def _modulated_weight(weight, style, scale, demodulate=True, transposed=False, e
     return w.reshape(b * o, i, kh, kw)
 
 
-def _modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, padding=1, eps=1e-8):
+def _modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, padding=1, eps=1e-8, bias=None, skip=None):
     """The REFERENCE formulation (networks.py:233-282): materialise per-sample filters, grouped convolution.
     Returns (out, None): demodulation is already inside the filters."""
     b, cin, h, w = x.shape
@@ -31,7 +31,12 @@ def _modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, 
         out = F.conv_transpose2d(xin, wt, padding=0, stride=2, groups=b)
     else:
         out = F.conv2d(xin, wt, padding=padding, groups=b)
-    return out.view(b, cout, out.shape[2], out.shape[3]), None
+    out = out.view(b, cout, out.shape[2], out.shape[3])
+    if bias is not None:       # ToRGB epilogue, reference networks.py:400-405
+        out = out + bias.type(out.dtype)
+    if skip is not None:
+        out = out.float() + skip
+    return out, None
 
 
 def _channel_scale(x, s):
