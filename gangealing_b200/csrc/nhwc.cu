@@ -133,14 +133,35 @@ rowwise_nhwc_kernel(float* __restrict__ out, float* __restrict__ partial, const 
 }
 
 // dst[r][c] = sum_k partial[(r*K + k)][c]    (r = sample for channel_scale; a single row for grad_bias)
-__global__ void nhwc_finish_kernel(float* __restrict__ dst, const float* __restrict__ partial, int64_t rows, int K, int C) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  const int64_t r = i / C;
-  const int c = static_cast<int>(i - r * C);
-  float acc = 0.f;
-  for (int k = 0; k < K; ++k) acc += partial[(r * K + k) * C + c];
-  dst[i] = acc;
+// CTA = 32 channels x 32 k-lanes: each lane sums every 32nd partial row (4 independent loads per trip), then the
+// 32 lane sums are combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024)
+nhwc_finish_kernel(float* __restrict__ dst, const float* __restrict__ partial, int64_t rows, int K, int C) {
+  __shared__ float red[32][33];
+  const int cblocks = (C + 31) / 32;
+  const int64_t r = blockIdx.x / cblocks;
+  const int c = (blockIdx.x - r * cblocks) * 32 + threadIdx.x;
+  const int ky = threadIdx.y;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < C) {
+    const float* base = partial + r * K * C + c;
+    int k = ky;
+    for (; k + 96 < K; k += 128) {
+      a0 += base[static_cast<int64_t>(k) * C];
+      a1 += base[static_cast<int64_t>(k + 32) * C];
+      a2 += base[static_cast<int64_t>(k + 64) * C];
+      a3 += base[static_cast<int64_t>(k + 96) * C];
+    }
+    for (; k < K; k += 32) a0 += base[static_cast<int64_t>(k) * C];
+  }
+  red[ky][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ky == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) t += red[q][threadIdx.x];
+    dst[r * C + c] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ to-RGB (1x1, 3 outputs)
@@ -573,7 +594,7 @@ static int launch_rowwise(int mode, float* out, float* dst, void* workspace, con
   if (dst) {
     const int64_t rows = per_sample ? N : 1;
     const int kk = per_sample ? K : static_cast<int>(N * K);
-    nhwc_finish_kernel<<<static_cast<unsigned>((rows * C + 255) / 256), 256, 0, st>>>(dst, partial, rows, kk, C);
+    nhwc_finish_kernel<<<static_cast<unsigned>(rows * ((C + 31) / 32)), dim3(32, 32), 0, st>>>(dst, partial, rows, kk, C);
     GG_CHECK_LAUNCH("nhwc finish launch");
   }
   return GG_OK;
@@ -638,7 +659,7 @@ int gg_to_rgb_nhwc_backward(float* gx, float* gwm, void* workspace, const float*
   to_rgb_nhwc_bwd_kernel<<<static_cast<unsigned>(grid), kT, smem, st>>>(gx, partial, g, x, wm, c4, HW, chunk, K);
   GG_CHECK_LAUNCH("to_rgb_nhwc backward launch");
   if (gwm) {
-    nhwc_finish_kernel<<<static_cast<unsigned>((N * 3 * C + 255) / 256), 256, 0, st>>>(gwm, partial, N, K, 3 * C);
+    nhwc_finish_kernel<<<static_cast<unsigned>(N * ((3 * C + 31) / 32)), dim3(32, 32), 0, st>>>(gwm, partial, N, K, 3 * C);
     GG_CHECK_LAUNCH("to_rgb_nhwc finish launch");
   }
   return GG_OK;

@@ -36,11 +36,57 @@ def timeit(fn, pools, iters=20, warmup=3):
     return st.elapsed_time(en) / iters
 
 
+def nhwc_family(B, dev, k4, timeit, report, pool_count):
+    """The channels-last kernels (csrc/nhwc.cu) at the generator's shapes."""
+    from gangealing_b200.op.modconv import channel_scale_raw, _ToRGB
+    CL = torch.channels_last
+    for C, H in [(128, 256), (256, 128), (512, 64), (512, 32), (512, 16), (512, 8)]:
+        hin = H + 1
+        nbytes = 4 * B * C * (hin * hin + H * H)
+        P = pool_count(nbytes)
+        xs = [torch.randn(B, C, hin, hin, device=dev).contiguous(memory_format=CL) for _ in range(P)]
+        noise = torch.randn(B, 1, H, H, device=dev)
+        nw = torch.tensor([0.1], device=dev)
+        bias = torch.randn(C, device=dev)
+        rs = torch.rand(B, C, device=dev) + 0.5
+        ms = timeit(lambda i: op.upfirdn2d(xs[i], k4, pad=(1, 1)), P)
+        report("nhwc blur C=%d %d->%d" % (C, hin, H), nbytes, ms)
+        ms = timeit(lambda i: op.blur_noise_bias_act(xs[i], k4, (1, 1), noise, nw, bias, row_scale=rs), P)
+        report("nhwc fused blur+noise+bias+act C=%d %d->%d" % (C, hin, H), nbytes + 4 * B * H * H, ms)
+        del xs
+        ys = [torch.randn(B, C, H, H, device=dev).contiguous(memory_format=CL) for _ in range(P)]
+        nb2 = 4 * B * C * H * H * 2
+        ms = timeit(lambda i: op.noise_bias_act(ys[i], noise, nw, bias, row_scale=rs), P)
+        report("nhwc noise+bias+act C=%d %d^2" % (C, H), nb2 + 4 * B * H * H, ms)
+        ms = timeit(lambda i: bias_act_backward_raw(ys[i], ys[(i + 1) % P], 0.2, 1.4, True), P)
+        report("nhwc bias_act backward(+bias grad) C=%d %d^2" % (C, H), 4 * B * C * H * H * 3, ms)
+        ms = timeit(lambda i: channel_scale_raw(ys[i], rs), P)
+        report("nhwc channel_scale C=%d %d^2" % (C, H), nb2, ms)
+        ms = timeit(lambda i: channel_scale_raw(ys[i], rs, y=ys[(i + 1) % P]), P)
+        report("nhwc channel_scale + row_dot C=%d %d^2" % (C, H), 4 * B * C * H * H * 3, ms)
+        wm = torch.randn(B, 3, C, device=dev)
+        b3 = torch.randn(1, 3, 1, 1, device=dev)
+        skip = torch.randn(B, 3, H, H, device=dev)
+        ms = timeit(lambda i: _ToRGB.apply(ys[i], wm, b3, skip), P)
+        report("nhwc to_rgb forward C=%d %d^2" % (C, H), 4 * B * H * H * (C + 6), ms)
+        g3 = torch.randn(B, 3, H, H, device=dev)
+        lib = __import__("gangealing_b200._lib", fromlist=["x"])
+        gx = torch.empty_like(ys[0]); gw = torch.empty(B, 3, C, device=dev)
+        ws = torch.empty(max(1, lib.load().gg_to_rgb_nhwc_workspace(B, C, H * H) // 4), device=dev)
+        ms = timeit(lambda i: lib.check(lib.load().gg_to_rgb_nhwc_backward(gx.data_ptr(), gw.data_ptr(), ws.data_ptr(), g3.data_ptr(),
+                    ys[i].data_ptr(), wm.data_ptr(), B, C, H * H, lib.stream()), "to_rgb bwd"), P)
+        report("nhwc to_rgb backward C=%d %d^2" % (C, H), 4 * B * H * H * (2 * C + 3), ms)
+        ms = timeit(lambda i: ys[(i + 1) % P].copy_(ys[i]), P)
+        report("  torch copy_ (roofline probe) C=%d %d^2" % (C, H), nb2, ms)
+        del ys
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=5)
     ap.add_argument("--json", default=None)
     ap.add_argument("--dtype", default="float32")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"])
     args = ap.parse_args()
     dt = getattr(torch, args.dtype)
     es = torch.empty(0, dtype=dt).element_size()
@@ -59,6 +105,13 @@ def main():
     def pool_count(nbytes):
         return max(2, min(8, int(400e6 // max(nbytes, 1)) + 1))
 
+    if args.layout == "nhwc":
+        nhwc_family(B, dev, k4, timeit, report, pool_count)
+        if args.json:
+            os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
+            json.dump({"batch": B, "dtype": "float32", "layout": "nhwc", "peak_gbs": peak, "peak_source": src, "rows": rows},
+                      open(args.json, "w"), indent=1)
+        return
     for C, H in [(128, 256), (256, 128), (512, 64), (512, 32), (512, 16), (512, 8)]:
         hin = H + 1
         nbytes = es * B * C * (hin * hin + H * H)
