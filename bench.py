@@ -85,7 +85,8 @@ def workload_config(args):
                         "perceptual VGG16 loss, Adam, EMA), synthetic latents + seeded random weights",
             "step_mode": "eager" if args.no_graph else "whole-step CUDA graph replay",
             "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "gen_size": 256, "flow_size": 128,
-            "parallelism": "dp%d" % args.gpus, "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB)"}
+            "parallelism": "dp%d" % args.gpus, "activation_layout": "NHWC (channels-last) generator + STN trunk",
+            "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB)"}
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
@@ -245,7 +246,9 @@ def run_ours(args):
         durs = [a.elapsed_time(b) for a, b, _ in sel]
         avg_ms = sum(durs) / len(durs)
         achieved = biggest / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "fir4_band_kernel<float,*,FUSED> (blur+noise+bias+lrelu, 256^2 layer)",
+        kname = ("blur_nhwc_kernel<FUSED=1,SEP=1> (channels-last blur+noise+bias+lrelu tail, 256^2 layer)" if cfg.channels_last
+                 else "fir4_band_kernel<float,*,FUSED> (blur+noise+bias+lrelu, 256^2 layer)")
+        roof = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch": biggest, "launches_timed": len(durs), "avg_launch_ms": avg_ms,
                 "peak_source": peak_src}

@@ -410,8 +410,37 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
     if (row_scale) rq = __ldg(reinterpret_cast<const float4*>(row_scale + static_cast<int64_t>(n) * p.c + c0) + cq);
     nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
   }
+  // lrelu(t)*gain == max(T, T*slope) with T = gain*t when gain > 0 and 0 <= slope <= 1: the gain is folded into the
+  // row scale, the bias and the noise weight, the row scale into the vertical taps (2 epilogue ops per output)
+  const bool fast = FUSED && p.gain > 0.f && ((p.act == 3 && p.alpha >= 0.f && p.alpha <= 1.f) || p.act == 1);
+  const float neg = (p.act == 3) ? p.alpha : 1.f;
+  if (fast) {
+    rq.x *= p.gain; rq.y *= p.gain; rq.z *= p.gain; rq.w *= p.gain;
+    bq.x *= p.gain; bq.y *= p.gain; bq.z *= p.gain; bq.w *= p.gain;
+    nw *= p.gain;
+  }
+  float4 kur[4];                           // vertical taps x row scale (separable fused path)
+#pragma unroll
+  for (int a = 0; a < 4; ++a) kur[a] = make_float4(ku[a] * rq.x, ku[a] * rq.y, ku[a] * rq.z, ku[a] * rq.w);
   const int xo = x_out0 + 2 * xg;         // first of this thread's two output columns
   const bool ok0 = xo < p.out_w, ok1 = xo + 1 < p.out_w;
+  // noise of the rows a stage completes is fetched one stage ahead (its latency hides behind the previous stage)
+  float nzn[kRY][2];
+#pragma unroll
+  for (int rr = 0; rr < kRY; ++rr) nzn[rr][0] = nzn[rr][1] = 0.f;
+  auto fetch_noise = [&](int it_) {
+#pragma unroll
+    for (int rr = 0; rr < kRY; ++rr) {
+      const int ro = it_ * kRY + rr - 3;
+      nzn[rr][0] = nzn[rr][1] = 0.f;
+      if (ro >= 0 && ro < rows_out) {
+        const float* np_ = noise + (static_cast<int64_t>(n) * p.out_h + oy0 + ro) * p.out_w + xo;
+        if (ok0) nzn[rr][0] = __ldg(np_);
+        if (ok1) nzn[rr][1] = __ldg(np_ + 1);
+      }
+    }
+  };
+  if (FUSED && noise) fetch_noise(0);
 
   // window: sep -> horizontal results hw[4 rows][2 cols] (float4 over channels); else raw inputs rw[4 rows][5 cols]
   float4 hw[SEP ? 4 : 1][2];
@@ -428,6 +457,10 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
         tma_load_4d(tiles + ns * kStageFloats, &tmap, c0, ix0, iy0 + nxt * kRY, n, &full_bar[ns]);
       }
     }
+    float nzc[kRY][2];
+#pragma unroll
+    for (int rr = 0; rr < kRY; ++rr) { nzc[rr][0] = nzn[rr][0]; nzc[rr][1] = nzn[rr][1]; }
+    if (FUSED && noise && it + 1 < n_stage_iters) fetch_noise(it + 1);
     mbar_wait(&full_bar[stage], static_cast<uint32_t>((it / kNS) & 1));
     const float* st = tiles + stage * kStageFloats;
 #pragma unroll
@@ -459,11 +492,20 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
         for (int j = 0; j < 2; ++j) {
           float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (SEP) {
+            if (FUSED) {                   // accumulate straight into row_scale*t + bias + noise (all x gain if `fast`)
+              const float nzj = nw * nzc[rr][j];
+              a4 = make_float4(bq.x + nzj, bq.y + nzj, bq.z + nzj, bq.w + nzj);
+            }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
               const float4 h = hw[(rr + 1 + a) & 3][j];   // rows r_in-3 .. r_in in order
-              a4.x = fmaf(ku[a], h.x, a4.x); a4.y = fmaf(ku[a], h.y, a4.y);
-              a4.z = fmaf(ku[a], h.z, a4.z); a4.w = fmaf(ku[a], h.w, a4.w);
+              if (FUSED) {
+                a4.x = fmaf(kur[a].x, h.x, a4.x); a4.y = fmaf(kur[a].y, h.y, a4.y);
+                a4.z = fmaf(kur[a].z, h.z, a4.z); a4.w = fmaf(kur[a].w, h.w, a4.w);
+              } else {
+                a4.x = fmaf(ku[a], h.x, a4.x); a4.y = fmaf(ku[a], h.y, a4.y);
+                a4.z = fmaf(ku[a], h.z, a4.z); a4.w = fmaf(ku[a], h.w, a4.w);
+              }
             }
           } else {
 #pragma unroll
@@ -474,26 +516,22 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
                 a4.x = fmaf(kf[a][b], v.x, a4.x); a4.y = fmaf(kf[a][b], v.y, a4.y);
                 a4.z = fmaf(kf[a][b], v.z, a4.z); a4.w = fmaf(kf[a][b], v.w, a4.w);
               }
+            if (FUSED) {
+              const float nzj = nw * nzc[rr][j];
+              a4.x = fmaf(a4.x, rq.x, bq.x + nzj); a4.y = fmaf(a4.y, rq.y, bq.y + nzj);
+              a4.z = fmaf(a4.z, rq.z, bq.z + nzj); a4.w = fmaf(a4.w, rq.w, bq.w + nzj);
+            }
+          }
+          if (FUSED) {
+            if (fast) {
+              a4.x = fmaxf(a4.x, a4.x * neg); a4.y = fmaxf(a4.y, a4.y * neg);
+              a4.z = fmaxf(a4.z, a4.z * neg); a4.w = fmaxf(a4.w, a4.w * neg);
+            } else {
+              a4.x = (a4.x > 0.f ? a4.x : a4.x * neg) * p.gain; a4.y = (a4.y > 0.f ? a4.y : a4.y * neg) * p.gain;
+              a4.z = (a4.z > 0.f ? a4.z : a4.z * neg) * p.gain; a4.w = (a4.w > 0.f ? a4.w : a4.w * neg) * p.gain;
+            }
           }
           acc[j] = a4;
-        }
-        if (FUSED) {
-          float nz0 = 0.f, nz1 = 0.f;
-          if (noise) {
-            const float* np_ = noise + (static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + xo;
-            if (ok0) nz0 = nw * __ldg(np_);
-            if (ok1) nz1 = nw * __ldg(np_ + 1);
-          }
-          const float neg = (p.act == 3) ? p.alpha : 1.f;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float nzj = j ? nz1 : nz0;
-            float t;
-            t = fmaf(acc[j].x, rq.x, bq.x) + nzj; acc[j].x = (t > 0.f ? t : t * neg) * p.gain;
-            t = fmaf(acc[j].y, rq.y, bq.y) + nzj; acc[j].y = (t > 0.f ? t : t * neg) * p.gain;
-            t = fmaf(acc[j].z, rq.z, bq.z) + nzj; acc[j].z = (t > 0.f ? t : t * neg) * p.gain;
-            t = fmaf(acc[j].w, rq.w, bq.w) + nzj; acc[j].w = (t > 0.f ? t : t * neg) * p.gain;
-          }
         }
         float* op = out + (((static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + xo) * p.c + c0) + cq * 4;
         if (ok0) *reinterpret_cast<float4*>(op) = acc[0];
