@@ -248,8 +248,15 @@ def run_ours(args):
         achieved = biggest / (avg_ms * 1e-3) / 1e9
         kname = ("blur_nhwc_kernel<FUSED=1,SEP=1> (channels-last blur+noise+bias+lrelu tail, 256^2 layer)" if cfg.channels_last
                  else "fir4_band_kernel<float,*,FUSED> (blur+noise+bias+lrelu, 256^2 layer)")
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (same shape and batch only)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_nhwc_b32_traffic.json")
+        if cfg.channels_last and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("per_gpu_batch") == args.batch:
+                traffic = tj["kernels"].get("blur_nhwc_kernel<1, 1>", {}).get("dram_bytes_per_launch")
         roof = {"bound": "hbm", "kernel": kname,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": biggest, "launches_timed": len(durs), "avg_launch_ms": avg_ms,
                 "peak_source": peak_src}
     cpu = None
