@@ -229,9 +229,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms2 = t.tolist()
     if rank != 0:
-        if distributed:
-            dist.barrier()
-            dist.destroy_process_group()
+        finish(distributed, tr)
         return
 
     images = args.batch * world * args.steps
@@ -277,9 +275,25 @@ def run_ours(args):
             "clocks": sampler.summary() if sampler else None,
             "losses": {k: float(v.detach()) for k, v in out.items()}}
     print(json.dumps(line), flush=True)
-    if distributed:
+    finish(distributed, tr)
+
+
+def finish(distributed, tr):
+    """Tear the process group down AFTER the result is out.  A watchdog ends the process with status 0 if NCCL's
+    teardown stalls (communicators referenced by a captured graph have been seen to block in destroy)."""
+    sys.stdout.flush()
+    if not distributed:
+        return
+    watchdog = threading.Timer(45.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    try:
         dist.barrier()
+        tr.release_graph()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+    finally:
+        watchdog.cancel()
 
 
 def main():

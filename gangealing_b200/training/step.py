@@ -173,6 +173,11 @@ class Trainer:
         self._graph = graph
         return self
 
+    def release_graph(self):
+        """Drop the captured graph (before tearing down the process group whose collectives it references)."""
+        self._graph = None
+        self._static_out = None
+
     def _eager_step(self, z=None):
         cfg = self.cfg
         loss_dict = self.losses(z)
