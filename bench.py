@@ -284,6 +284,7 @@ def finish(distributed, tr):
     sys.stdout.flush()
     if not distributed:
         return
+    import torch.distributed as dist
     watchdog = threading.Timer(45.0, lambda: os._exit(0))
     watchdog.daemon = True
     watchdog.start()
