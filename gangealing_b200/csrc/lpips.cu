@@ -1,0 +1,236 @@
+// lpips.cu -- the perceptual loss's front end on channels-last feature maps (sm_100a), SURVEY.md 8(f) rank 2.
+//
+// reference: models/losses/lpips.py:26-28 (`normalize_tensor`: f / (sqrt(sum_c f^2) + 1e-10)), :193-195
+// (`diffs = (feats0 - feats1)**2`), :197-205 (`lins[kk](diffs)` = per-channel weights, or `.sum(dim=1)`), :226
+// (`spatial_average` = mean over H, W).  The reference spends ~14 ATen passes per VGG layer forward (and ~25 backward)
+// on five feature maps x two images every step; here ONE pass forward (reads both maps) and ONE pass backward
+// (reads both maps, writes both gradients):
+//     d[n] = 1/HW * sum_p sum_c w[c] * (a[n,p,c]/(|a[n,p,:]|+eps) - b[n,p,c]/(|b[n,p,:]|+eps))^2
+// A group of L = min(32, C/4) lanes owns one pixel: every lane keeps its channel quads of both maps in registers
+// (<= 8 independent 128-bit loads in flight), the per-pixel sums are butterfly reductions inside the group, and the
+// difference is formed from the normalised values themselves (no |a|^2 + |b|^2 - 2ab cancellation).
+#include "common.cuh"
+
+namespace gg {
+namespace {
+
+constexpr int kT = 256;
+constexpr int kMaxTrips = 8;     // C <= 4 * 32 * 8 = 1024
+
+template <int L>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int m = L / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(mask, v, m);
+  return v;
+}
+
+// TRIPS channel quads per lane (compile time): registers, no local memory.
+template <int L, int TRIPS, bool BACKWARD>
+__global__ void __launch_bounds__(kT)
+feature_distance_kernel(float* __restrict__ partial, float* __restrict__ g0, float* __restrict__ g1,
+                        const float* __restrict__ gout, const float* __restrict__ f0, const float* __restrict__ f1,
+                        const float* __restrict__ w, int c4, int64_t hw, int chunk, int chunks_per_sample, float eps,
+                        float inv_hw) {
+  __shared__ float red[kT / 32];
+  const int64_t n = blockIdx.x / chunks_per_sample;
+  const int ck = blockIdx.x - n * chunks_per_sample;
+  const int64_t p0 = static_cast<int64_t>(ck) * chunk, p1 = min(p0 + chunk, hw);
+  constexpr int GROUPS = kT / L;                    // pixels in flight per CTA
+  const int l = threadIdx.x % L, grp = threadIdx.x / L;
+  const int lane = threadIdx.x & 31;
+  const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (lane / L * L));
+  float4 wq[TRIPS];
+#pragma unroll
+  for (int t = 0; t < TRIPS; ++t)
+    wq[t] = w ? __ldg(reinterpret_cast<const float4*>(w) + l + t * L) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float gs = BACKWARD ? 2.f * __ldg(gout + n) * inv_hw : 0.f;
+  float acc = 0.f;
+  for (int64_t p = p0 + grp; p < p1; p += GROUPS) {
+    const int64_t base = (n * hw + p) * c4;
+    const float4* ap = reinterpret_cast<const float4*>(f0) + base;
+    const float4* bp = reinterpret_cast<const float4*>(f1) + base;
+    float4 a[TRIPS], b[TRIPS];
+#pragma unroll
+    for (int t = 0; t < TRIPS; ++t) a[t] = __ldcs(ap + l + t * L);
+#pragma unroll
+    for (int t = 0; t < TRIPS; ++t) b[t] = __ldcs(bp + l + t * L);
+    float saa = 0.f, sbb = 0.f;
+#pragma unroll
+    for (int t = 0; t < TRIPS; ++t) {
+      saa = fmaf(a[t].x, a[t].x, fmaf(a[t].y, a[t].y, fmaf(a[t].z, a[t].z, fmaf(a[t].w, a[t].w, saa))));
+      sbb = fmaf(b[t].x, b[t].x, fmaf(b[t].y, b[t].y, fmaf(b[t].z, b[t].z, fmaf(b[t].w, b[t].w, sbb))));
+    }
+    saa = group_sum<L>(saa, gmask);
+    sbb = group_sum<L>(sbb, gmask);
+    const float ra = sqrtf(saa), rb = sqrtf(sbb);
+    const float ia = 1.f / (ra + eps), ib = 1.f / (rb + eps);
+    if (!BACKWARD) {
+      float d = 0.f;
+#pragma unroll
+      for (int t = 0; t < TRIPS; ++t) {
+        const float dx = a[t].x * ia - b[t].x * ib, dy = a[t].y * ia - b[t].y * ib;
+        const float dz = a[t].z * ia - b[t].z * ib, dw = a[t].w * ia - b[t].w * ib;
+        d = fmaf(wq[t].x * dx, dx, fmaf(wq[t].y * dy, dy, fmaf(wq[t].z * dz, dz, fmaf(wq[t].w * dw, dw, d))));
+      }
+      acc += d;                                     // lanes of a group hold partial sums; reduced once per CTA
+    } else {
+      // t_c = w_c (a^_c - b^_c);  Pa = sum t_c a_c;  Pb = sum t_c b_c
+      float4 tq[TRIPS];
+      float pa = 0.f, pb = 0.f;
+#pragma unroll
+      for (int t = 0; t < TRIPS; ++t) {
+        tq[t].x = wq[t].x * (a[t].x * ia - b[t].x * ib); tq[t].y = wq[t].y * (a[t].y * ia - b[t].y * ib);
+        tq[t].z = wq[t].z * (a[t].z * ia - b[t].z * ib); tq[t].w = wq[t].w * (a[t].w * ia - b[t].w * ib);
+        pa = fmaf(tq[t].x, a[t].x, fmaf(tq[t].y, a[t].y, fmaf(tq[t].z, a[t].z, fmaf(tq[t].w, a[t].w, pa))));
+        pb = fmaf(tq[t].x, b[t].x, fmaf(tq[t].y, b[t].y, fmaf(tq[t].z, b[t].z, fmaf(tq[t].w, b[t].w, pb))));
+      }
+      pa = group_sum<L>(pa, gmask);
+      pb = group_sum<L>(pb, gmask);
+      // d a^_c / d a_k = delta_ck * ia - a_c a_k * ia^2 / ra.  At an all-zero pixel the reference's autograd yields
+      // nan (sqrt'(0) * 0 = inf * 0); the gradient of that pixel is DEFINED as 0 here (a dead pixel gets no signal).
+      const float ka = ra > 0.f ? pa * ia * ia / ra : 0.f;
+      const float kb = rb > 0.f ? pb * ib * ib / rb : 0.f;
+      const float gsa = ra > 0.f ? gs : 0.f, gsb = rb > 0.f ? gs : 0.f;
+      float4* g0p = reinterpret_cast<float4*>(g0) + base;
+      float4* g1p = reinterpret_cast<float4*>(g1) + base;
+#pragma unroll
+      for (int t = 0; t < TRIPS; ++t) {
+        float4 o;
+        if (g0) {
+          o.x = gsa * (tq[t].x * ia - a[t].x * ka); o.y = gsa * (tq[t].y * ia - a[t].y * ka);
+          o.z = gsa * (tq[t].z * ia - a[t].z * ka); o.w = gsa * (tq[t].w * ia - a[t].w * ka);
+          g0p[l + t * L] = o;
+        }
+        if (g1) {
+          o.x = -gsb * (tq[t].x * ib - b[t].x * kb); o.y = -gsb * (tq[t].y * ib - b[t].y * kb);
+          o.z = -gsb * (tq[t].z * ib - b[t].z * kb); o.w = -gsb * (tq[t].w * ib - b[t].w * kb);
+          g1p[l + t * L] = o;
+        }
+      }
+    }
+  }
+  if (!BACKWARD) {
+    acc = warp_sum(acc);
+    if (lane == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < kT / 32; ++i) t += red[i];
+      partial[blockIdx.x] = t * inv_hw;
+    }
+  }
+}
+
+__global__ void distance_finish_kernel(float* __restrict__ out, const float* __restrict__ partial, int64_t N, int K) {
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int k = 0; k < K; ++k) t += partial[n * K + k];
+  out[n] = t;
+}
+
+int64_t distance_chunk(int64_t N, int64_t HW, int groups) {
+  const int64_t target = 8LL * sm_count();
+  int64_t k = (target + N - 1) / N;
+  const int64_t kmax = (HW + 2 * groups - 1) / (2 * groups);
+  if (k > kmax) k = kmax;
+  if (k > 64) k = 64;                      // the finish kernel sums K partials serially
+  if (k < 1) k = 1;
+  return (HW + k - 1) / k;
+}
+
+template <bool BACKWARD>
+int launch_distance(float* partial, float* g0, float* g1, const float* gout, const float* f0, const float* f1,
+                    const float* w, int64_t N, int C, int64_t HW, float eps, cudaStream_t st, int* k_out) {
+  const int c4 = C / 4;
+  const int L = c4 >= 32 ? 32 : c4;         // c4 is a power of two here when < 32 (checked by the caller)
+  const int trips = c4 / L;
+  const int64_t chunk64 = distance_chunk(N, HW, kT / L);
+  const int chunk = static_cast<int>(chunk64);
+  const int K = static_cast<int>((HW + chunk - 1) / chunk);
+  if (k_out) *k_out = K;
+  const unsigned grid = static_cast<unsigned>(N * K);
+  const float inv_hw = 1.f / static_cast<float>(HW);
+#define GG_DIST(L_, T_)                                                                                          \
+  feature_distance_kernel<L_, T_, BACKWARD><<<grid, kT, 0, st>>>(partial, g0, g1, gout, f0, f1, w, c4, HW, chunk, K, \
+                                                                 eps, inv_hw)
+  if (L == 32) {
+    switch (trips) {
+      case 1: GG_DIST(32, 1); break;
+      case 2: GG_DIST(32, 2); break;
+      case 3: GG_DIST(32, 3); break;
+      case 4: GG_DIST(32, 4); break;
+      case 6: GG_DIST(32, 6); break;
+      case 8: GG_DIST(32, 8); break;
+      default: return fail(GG_ERR_UNSUPPORTED, "feature_distance: C = %d is not a supported channel count", C);
+    }
+  } else if (L == 16) { GG_DIST(16, 1); }
+  else if (L == 8) { GG_DIST(8, 1); }
+  else if (L == 4) { GG_DIST(4, 1); }
+  else if (L == 2) { GG_DIST(2, 1); }
+  else { GG_DIST(1, 1); }
+#undef GG_DIST
+  return GG_OK;
+}
+
+int check_distance(const char* who, int64_t N, int C, int64_t HW) {
+  if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "%s: negative size", who);
+  if (C % 4 != 0 || C > 4 * 32 * kMaxTrips) return fail(GG_ERR_UNSUPPORTED, "%s: C must be a multiple of 4, <= 1024", who);
+  const int c4 = C / 4;
+  if (c4 < 32 && (c4 & (c4 - 1)) != 0) return fail(GG_ERR_UNSUPPORTED, "%s: C < 128 must be a power of two", who);
+  if (c4 >= 32 && c4 % 32 != 0) return fail(GG_ERR_UNSUPPORTED, "%s: C >= 128 must be a multiple of 128", who);
+  if (N * HW > 0 && (HW + 0) > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "%s: plane too large", who);
+  return GG_OK;
+}
+
+}  // namespace
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int64_t gg_feature_distance_workspace(int64_t N, int C, int64_t HW) {
+  if (N <= 0 || C < 4 || HW <= 0) return 0;
+  const int c4 = C / 4;
+  const int L = c4 >= 32 ? 32 : c4;
+  const int64_t chunk = distance_chunk(N, HW, kT / (L > 0 ? L : 1));
+  return N * ((HW + chunk - 1) / chunk) * static_cast<int64_t>(sizeof(float));
+}
+
+int gg_feature_distance_forward(float* out, void* workspace, const float* f0, const float* f1, const float* weight,
+                                int64_t N, int C, int64_t HW, float eps, void* stream) {
+  int rc = check_distance("feature_distance", N, C, HW);
+  if (rc != GG_OK) return rc;
+  if (N == 0) return GG_OK;
+  if (!out) return fail(GG_ERR_BAD_ARG, "feature_distance: null output");
+  auto st = static_cast<cudaStream_t>(stream);
+  if (C == 0 || HW == 0) {   // mean over an empty set is undefined in the reference (nan); keep zeros
+    cudaError_t e = cudaMemsetAsync(out, 0, N * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "feature_distance memset");
+    return GG_OK;
+  }
+  if (!f0 || !f1 || !workspace) return fail(GG_ERR_BAD_ARG, "feature_distance: null tensor");
+  int K = 1;
+  rc = launch_distance<false>(static_cast<float*>(workspace), nullptr, nullptr, nullptr, f0, f1, weight, N, C, HW, eps, st, &K);
+  if (rc != GG_OK) return rc;
+  GG_CHECK_LAUNCH("feature_distance forward launch");
+  distance_finish_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(out, static_cast<const float*>(workspace), N, K);
+  GG_CHECK_LAUNCH("feature_distance finish launch");
+  return GG_OK;
+}
+
+int gg_feature_distance_backward(float* g0, float* g1, const float* grad_out, const float* f0, const float* f1,
+                                 const float* weight, int64_t N, int C, int64_t HW, float eps, void* stream) {
+  int rc = check_distance("feature_distance backward", N, C, HW);
+  if (rc != GG_OK) return rc;
+  if (N * HW == 0 || C == 0) return GG_OK;
+  if (!grad_out || !f0 || !f1 || (!g0 && !g1)) return fail(GG_ERR_BAD_ARG, "feature_distance backward: null tensor");
+  rc = launch_distance<true>(nullptr, g0, g1, grad_out, f0, f1, weight, N, C, HW, eps, static_cast<cudaStream_t>(stream), nullptr);
+  if (rc != GG_OK) return rc;
+  GG_CHECK_LAUNCH("feature_distance backward launch");
+  return GG_OK;
+}
+
+}  // extern "C"

@@ -6,6 +6,8 @@ for the SimCLR checkpoint, exactly as BASELINE.md section 3 prescribes for the o
 import torch
 import torch.nn as nn
 
+from ..op.feature_distance import feature_distance
+
 _VGG16_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _SLICE_ENDS = (4, 9, 16, 23, 30)  # relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 in torchvision's layer numbering
 
@@ -61,7 +63,9 @@ class PerceptualLoss(nn.Module):
         f1 = self.net(((in1 - self.shift) / self.scale).contiguous(memory_format=cl))
         val = 0
         for a, b in zip(f0, f1):
-            val = val + ((self._unit(a) - self._unit(b)) ** 2).sum(dim=1, keepdim=True).mean([2, 3], keepdim=True)
+            # normalise, difference, channel sum and spatial mean in one pass over both maps (csrc/lpips.cu) on
+            # channels-last CUDA features; the same formula with tensor ops elsewhere (lpips.py:193-205, :226)
+            val = val + feature_distance(a, b)
         return val / self.divisor
 
 

@@ -307,7 +307,38 @@ def gen_losses(ref_models):
     _save("losses", **out)
 
 
-EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses]
+def gen_perceptual(ref_models):
+    """Front end of the perceptual loss: the reference's normalize_tensor / NetLinLayer /
+    spatial_average (models/losses/lpips.py:26-28, :197-205, :226, :238-247) on seeded relu-like feature maps."""
+    import models.losses.lpips as L
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for name, (n, c, h, w), weighted in (("c64", (2, 64, 8, 8), False), ("c128_w", (2, 128, 5, 7), True),
+                                         ("c512", (1, 512, 3, 4), False), ("c256_w", (3, 256, 4, 4), True),
+                                         ("c8", (2, 8, 6, 6), False)):
+        f0 = torch.relu(torch.randn(n, c, h, w, generator=g)).requires_grad_(True)
+        f1 = torch.relu(torch.randn(n, c, h, w, generator=g) + 0.3).requires_grad_(True)
+        with torch.no_grad():
+            f0[0, :, 0, 0] = 0.0            # an all-zero pixel in ONE map: |f| = 0 -> f/(0+eps) = 0 in the forward
+        diff = (L.normalize_tensor(f0) - L.normalize_tensor(f1)) ** 2
+        if weighted:
+            lin = L.NetLinLayer(c, use_dropout=False)
+            wv = torch.rand(c, generator=g)
+            with torch.no_grad():
+                lin.model[-1].weight.copy_(wv.reshape(1, c, 1, 1))
+            res = L.spatial_average(lin(diff), keepdim=True)
+            out[name + ".weight"] = wv
+        else:
+            res = L.spatial_average(diff.sum(dim=1, keepdim=True), keepdim=True)
+        go = torch.randn(res.shape, generator=g)
+        g0, g1 = torch.autograd.grad(res, [f0, f1], go)
+        # the reference's sqrt backward is nan at an all-zero pixel (inf * 0); the fixture stores the finite remainder
+        out[name + ".f0"], out[name + ".f1"], out[name + ".out"], out[name + ".gout"] = f0.detach(), f1.detach(), res.detach(), go
+        out[name + ".g0"], out[name + ".g1"] = torch.nan_to_num(g0, nan=0.0), g1
+    _save("perceptual", **out)
+
+
+EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual]
 
 if __name__ == "__main__":
     main()
