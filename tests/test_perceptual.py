@@ -76,4 +76,4 @@ def test_fused_kernels_match_oracle(shape):
     assert_close(gy, gbo, rtol=1e-4, what="g1")
     # symmetry and identity: d(a, b) == d(b, a), d(a, a) == 0 -- size-independent properties
     assert_close(feature_distance(y, x), r, rtol=1e-6)
-    assert float(feature_distance(x, x).abs().max()) == 0.0
+    assert float(feature_distance(x, x).abs().max()) < 1e-12   # a*ia - b*ib contracts to an fma: one rounding residual
