@@ -44,6 +44,8 @@ SIGNATURES = {
     "gg_channel_scale_nhwc": (_I, [_P] * 6 + [_L, _I, _L, _P]),
     "gg_bias_act_backward_nhwc": (_I, [_P] * 5 + [_F, _F, _L, _I, _L, _P]),
     "gg_blur_nhwc": (_I, [_P] * 7 + [_L] + [_I] * 12 + [_F, _F, _P]),
+    "gg_tent_downsample_forward": (_I, [_P] * 4 + [_L, _I, _I, _I, _I, _P]),
+    "gg_tent_downsample_backward": (_I, [_P] * 4 + [_L, _I, _I, _I, _I, _P]),
     "gg_feature_distance_workspace": (_L, [_L, _I, _L]),
     "gg_feature_distance_forward": (_I, [_P] * 5 + [_L, _I, _L, _F, _P]),
     "gg_feature_distance_backward": (_I, [_P] * 6 + [_L, _I, _L, _F, _P]),

@@ -112,9 +112,48 @@ def mipmap_warp(inputs, grid, max_num_levels=8, min_level=0.0, padding_mode="bor
     return out, levels
 
 
+class _TentDownsample(Function):
+    """BilinearDownsample as one gather kernel (csrc/resample.cu); backward = its exact adjoint."""
+
+    @staticmethod
+    def forward(ctx, input, taps_h, taps_v, stride):
+        _lib.require_cuda(input, taps_h, taps_v)
+        x = input.contiguous()
+        n, c, h, w = x.shape
+        p = stride // 2
+        oh, ow = (h + 2 * p - 2 * stride) // stride + 1, (w + 2 * p - 2 * stride) // stride + 1
+        out = torch.empty((n, c, max(oh, 0), max(ow, 0)), dtype=x.dtype, device=x.device)
+        rc = _lib.load().gg_tent_downsample_forward(out.data_ptr(), x.data_ptr(), taps_h.data_ptr(), taps_v.data_ptr(),
+                                                    n, c, h, w, stride, _lib.stream())
+        _lib.check(rc, "gg_tent_downsample_forward")
+        ctx.save_for_backward(taps_h, taps_v)
+        ctx.cfg = (stride, tuple(x.shape))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        taps_h, taps_v = ctx.saved_tensors
+        stride, (n, c, h, w) = ctx.cfg
+        g = grad_output.contiguous()
+        gin = torch.empty((n, c, h, w), dtype=g.dtype, device=g.device)
+        rc = _lib.load().gg_tent_downsample_backward(gin.data_ptr(), g.data_ptr(), taps_h.data_ptr(), taps_v.data_ptr(),
+                                                     n, c, h, w, stride, _lib.stream())
+        _lib.check(rc, "gg_tent_downsample_backward")
+        return gin, None, None, None
+
+
 def bilinear_downsample(input, stride, kernel_horz, kernel_vert):
-    """Functional form of BilinearDownsample.forward (reflect-pad + separable tent filter with stride)."""
+    """Functional form of BilinearDownsample.forward (reference antialiased_sampling.py:254-256): reflect-pad +
+    separable tent filter with stride.  fp32 images take the single-kernel path; other dtypes the two depthwise
+    convolutions of the reference."""
     channels = input.shape[1]
+    if input.dtype == torch.float32 and input.dim() == 4 and 2 * stride <= 32:
+        taps = 2 * stride
+        th = kernel_horz.reshape(channels, taps).float().contiguous()
+        tv = kernel_vert.reshape(channels, taps).float().contiguous()
+        return _TentDownsample.apply(input, th, tv, int(stride))
+    _lib.require_cuda(input)
     pad = int(stride / 2)
     x = F.pad(input, (pad, pad, pad, pad), mode="reflect")
     rows = F.conv2d(x, kernel_horz, stride=(1, stride), groups=channels)
@@ -178,7 +217,8 @@ class MipmapWarp(nn.Module):
 
 class BilinearDownsample(nn.Module):
     """Reflect-pad + separable tent filter with stride (reference antialiased_sampling.py:241-256).
-    Same buffers (`kernel_horz`, `kernel_vert`); SURVEY.md 8(f) rank 1 -- still two cuDNN depthwise convs here."""
+    Same buffers (`kernel_horz`, `kernel_vert`); on sm_100a one gather kernel (csrc/resample.cu) instead of pad + two
+    depthwise convolutions."""
 
     def __init__(self, stride, channels, ops=None):
         super().__init__()

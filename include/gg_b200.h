@@ -276,6 +276,17 @@ GG_API int gg_feature_distance_forward(float* out, void* workspace, const float*
 GG_API int gg_feature_distance_backward(float* g0, float* g1, const float* grad_out, const float* f0, const float* f1,
                                         const float* weight, int64_t N, int C, int64_t HW, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * BilinearDownsample: reference models/spatial_transformers/antialiased_sampling.py:241-256 --
+ * ReflectionPad2d(stride/2) + depthwise 1x2s conv, stride (1,s) + depthwise 2sx1 conv, stride (s,1).  One gather:
+ *   out[m,oy,ox] = sum_i sum_j taps_v[c][i] taps_h[c][j] in[m, R(oy*s+i-p), R(ox*s+j-p)],  p = s/2, R = reflection
+ * in: (N, C, in_h, in_w) fp32 NCHW; taps_h / taps_v: (C, 2*stride) (the module's `kernel_horz` / `kernel_vert` buffers);
+ * out: (N, C, (in_h+2p-2s)/s+1, (in_w+2p-2s)/s+1).  backward = the exact adjoint, gather form (deterministic). */
+GG_API int gg_tent_downsample_forward(float* out, const float* in, const float* taps_h, const float* taps_v, int64_t N,
+                                      int C, int in_h, int in_w, int stride, void* stream);
+GG_API int gg_tent_downsample_backward(float* grad_in, const float* grad_out, const float* taps_h, const float* taps_v,
+                                       int64_t N, int C, int in_h, int in_w, int stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

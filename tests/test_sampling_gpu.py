@@ -102,3 +102,37 @@ def test_bilinear_downsample_golden():
     for stride in (2, 4):
         y = stn.BilinearDownsample(stride, 3).to(DEV)(blob["x"].to(DEV))
         assert_close(y, blob["s%d.y" % stride], rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape,stride", [((2, 3, 32, 32), 2), ((1, 3, 33, 29), 2), ((2, 3, 64, 48), 4), ((1, 2, 40, 40), 8),
+                                          ((2, 3, 9, 7), 1), ((1, 3, 21, 30), 3), ((4, 3, 256, 256), 2)])
+def test_bilinear_downsample_forward_and_adjoint(shape, stride):
+    """One-kernel BilinearDownsample vs the oracle (reference antialiased_sampling.py:241-256): forward, and the
+    gather-form backward against autograd of the reference formulation."""
+    stn = _stn()
+    g = torch.Generator().manual_seed(shape[2] * 7 + stride)
+    x = torch.randn(*shape, generator=g)
+    xo = x.clone().requires_grad_(True)
+    yo = S.bilinear_downsample_ref(xo, stride)
+    go = torch.randn(yo.shape, generator=g)
+    (gxo,) = torch.autograd.grad(yo, xo, go)
+    mod = stn.BilinearDownsample(stride, shape[1]).to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    y = mod(xg)
+    assert y.shape == yo.shape
+    assert_close(y, yo, rtol=1e-5, what="forward")
+    (gx,) = torch.autograd.grad(y, xg, go.to(DEV))
+    assert_close(gx, gxo, rtol=1e-5, what="backward")
+    lhs = (y.detach().double() * go.to(DEV).double()).sum()
+    rhs = (xg.detach().double() * gx.double()).sum()
+    assert abs(lhs - rhs) <= 1e-6 * (y.detach().double() * go.to(DEV).double()).abs().sum()
+
+
+def test_bilinear_downsample_errors():
+    stn = _stn()
+    with pytest.raises(RuntimeError):
+        stn.BilinearDownsample(2, 3)(torch.zeros(1, 3, 8, 8))             # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        stn.BilinearDownsample(4, 3).to(DEV)(torch.zeros(1, 3, 2, 2, device=DEV))   # plane not larger than stride/2
+    y = stn.BilinearDownsample(2, 3).to(DEV)(torch.zeros(0, 3, 8, 8, device=DEV))
+    assert y.shape == (0, 3, 4, 4)
