@@ -80,6 +80,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+_T0 = time.time()
+
+
+def phase(msg):
+    """Rank-0 progress line on stderr (wall clock since start): where a slow launch spends its time."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench %7.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def workload_config(args):
     return {"workload": "LSUN Cats 256^2 train.py step (StyleGAN2-256 generator + unimodal similarity+flow STN @128, "
                         "perceptual VGG16 loss, Adam, EMA), synthetic latents + seeded random weights",
@@ -149,8 +158,10 @@ def run_ours(args):
     rank = gdist.get_rank()
     torch.backends.cudnn.benchmark = True
 
+    phase("process group ready (world %d)" % world)
     cfg = TrainConfig(batch=args.batch)
     tr = Trainer(cfg, dev, distributed=distributed)
+    phase("trainer built")
 
     def sync_all():
         torch.cuda.synchronize()
@@ -161,6 +172,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         tr.step()
     sync_all()
+    phase("eager warm-up done")
 
     # ---- roofline probe: the dominant hand-written kernel (fused blur+noise+bias+lrelu tail) timed with CUDA
     #      events on its launching stream, inside real training steps of this workload (eager, so that the events
@@ -178,6 +190,7 @@ def run_ours(args):
     if use_graph:
         try:
             tr.capture(warmup=2)
+            phase("step captured as a CUDA graph")
             for _ in range(2):
                 tr.step()
         except Exception as exc:  # keep the bench alive: fall back to eager steps and say so
@@ -205,6 +218,7 @@ def run_ours(args):
     if profile:
         torch.cuda.cudart().cudaProfilerStop()
     ms = st.elapsed_time(en)
+    phase("timed region 1 done")
     calls = calls_per_step * args.steps
     if sampler:
         sampler.stop_flag.set()
@@ -275,7 +289,9 @@ def run_ours(args):
             "clocks": sampler.summary() if sampler else None,
             "losses": {k: float(v.detach()) for k, v in out.items()}}
     print(json.dumps(line), flush=True)
+    phase("result printed")
     finish(distributed, tr)
+    phase("process group torn down")
 
 
 def finish(distributed, tr):
@@ -285,7 +301,7 @@ def finish(distributed, tr):
     if not distributed:
         return
     import torch.distributed as dist
-    watchdog = threading.Timer(45.0, lambda: os._exit(0))
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
     watchdog.daemon = True
     watchdog.start()
     try:

@@ -16,7 +16,10 @@ def setup_distributed(backend="nccl"):
     if backend == "nccl":
         torch.cuda.set_device(local_rank)
     if not dist.is_initialized():
-        dist.init_process_group(backend=backend, init_method="env://")
+        if backend == "nccl":   # bind the communicator to this rank's device up front (no device guessing at the first barrier)
+            dist.init_process_group(backend=backend, init_method="env://", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend=backend, init_method="env://")
     synchronize()
     return True
 
