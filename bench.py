@@ -116,7 +116,7 @@ def cpu_step_rate(batch, steps=1, warmup=0):
     t0 = time.perf_counter()
     for _ in range(steps):
         out = tr.step()
-    float(out["p"])
+    float(out["p"].detach())
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps
 
