@@ -67,7 +67,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         if not self.samples:
