@@ -338,7 +338,33 @@ def gen_perceptual(ref_models):
     _save("perceptual", **out)
 
 
-EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual]
+def gen_points(ref_models):
+    """Point transfer: the reference's congeal_points / uncongeal_points /
+    transfer_points (spatial_transformer.py:631-726) for a similarity-only and a composed similarity+flow STN on CPU.
+    congeal_points on a flow STN is integer work (argmin + unravel_index): stored for exact comparison."""
+    from oracle import opset
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from models.spatial_transformers.spatial_transformer import get_stn
+    gen = torch.Generator().manual_seed(6100)
+    out = {}
+    for transforms in (["similarity"], ["similarity", "flow"]):
+        tag = "pts_" + "_".join(transforms)
+        stn = get_stn(list(transforms), flow_size=64, supersize=64, channel_multiplier=0.25, num_heads=1).eval()
+        opset.fill_parameters(stn, 21, gain=0.3)
+        img_a = torch.randn(2, 3, 64, 64, generator=gen)
+        img_b = torch.randn(2, 3, 64, 64, generator=gen)
+        pts = torch.rand(2, 9, 2, generator=gen) * 40.0 + 12.0          # pixel coordinates well inside the image
+        with torch.no_grad():
+            congealed = stn.congeal_points(img_a, pts)
+            back = stn.uncongeal_points(img_b, congealed.float() if congealed.dtype != torch.float32 else congealed,
+                                        normalize_input_points=congealed.dtype != torch.float32)
+            moved = stn.transfer_points(img_a, img_b, pts)
+        out[tag + ".img_a"], out[tag + ".img_b"], out[tag + ".points"] = img_a, img_b, pts
+        out[tag + ".congealed"], out[tag + ".uncongealed"], out[tag + ".transferred"] = congealed, back, moved
+    _save("points", **out)
+
+
+EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual, gen_points]
 
 if __name__ == "__main__":
     main()

@@ -94,3 +94,28 @@ def test_train_step_runs_and_learns_on_cpu_oracle_ops():
     assert any(not torch.equal(a, b) for a, b in zip(ema_before, tr.t_ema.parameters()))
     assert all(p.grad is None for p in tr.generator.parameters())  # G is frozen
     assert tr.ll_module.coefficients.grad is not None               # pass #2 of G is differentiated
+
+
+@pytest.mark.parametrize("transforms", [("similarity",), ("similarity", "flow")])
+def test_point_transfer_matches_reference_fixture(transforms):
+    """congeal_points / uncongeal_points / transfer_points (reference spatial_transformer.py:631-720), SURVEY.md 8(a13):
+    the nearest-neighbour indices of the flow STN (argmin + unravel_index) must match EXACTLY."""
+    from gangealing_b200.stn import get_stn
+    blob = load_golden("points")
+    tag = "pts_" + "_".join(transforms)
+    stn = get_stn(list(transforms), flow_size=64, supersize=64, channel_multiplier=0.25, num_heads=1, ops=CPU).eval()
+    opset.fill_parameters(stn, 21, gain=0.3)
+    img_a, img_b, pts = blob[tag + ".img_a"], blob[tag + ".img_b"], blob[tag + ".points"]
+    with torch.no_grad():
+        congealed = stn.congeal_points(img_a, pts)
+        is_index = congealed.dtype != torch.float32
+        back = stn.uncongeal_points(img_b, congealed.float() if is_index else congealed, normalize_input_points=is_index)
+        moved = stn.transfer_points(img_a, img_b, pts)
+    ref = blob[tag + ".congealed"]
+    assert congealed.dtype == ref.dtype and congealed.shape == ref.shape
+    if is_index:
+        assert torch.equal(congealed, ref), "nearest-neighbour indices differ from the reference"
+    else:
+        assert_close(congealed, ref, rtol=1e-5, what="congealed points")
+    assert_close(back, blob[tag + ".uncongealed"], rtol=1e-5, what="uncongealed points")
+    assert_close(moved, blob[tag + ".transferred"], rtol=1e-5, what="transferred points")
