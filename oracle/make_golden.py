@@ -364,7 +364,59 @@ def gen_points(ref_models):
     _save("points", **out)
 
 
-EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual, gen_points]
+STN_OPTION_CASES = [
+    # name, transforms, heads, call kwargs (tensors are created by the generator / the test from the same seeds)
+    ("iters3", ["similarity"], 1, dict(iters=3, return_warp=True, return_flow=True, padding_mode="border")),
+    ("composed_iters2_alpha", ["similarity", "flow"], 1, dict(iters=2, alpha=[0.35, 0.8], return_warp=True, return_flow=True,
+                                                              return_sim=True, padding_mode="reflection")),
+    ("composed_outres", ["similarity", "flow"], 1, dict(output_resolution=96, return_warp=True, return_flow=True,
+                                                         padding_mode="zeros")),
+    ("heads2_cartesian", ["similarity", "flow"], 2, dict(return_warp=True, return_flow=True, padding_mode="border")),
+    ("heads2_unfold", ["similarity", "flow"], 2, dict(unfold=True, return_warp=True, return_flow=True, padding_mode="border")),
+    ("intermediates", ["similarity", "flow"], 1, dict(return_intermediates=True, padding_mode="border")),
+]
+
+
+def stn_option_kwargs(kw):
+    """Case-table kwargs -> call kwargs (per-sample alpha is a tensor, warping_heads.py:244)."""
+    kw = dict(kw)
+    if isinstance(kw.get("alpha"), list):
+        kw["alpha"] = torch.tensor(kw["alpha"])
+    return kw
+
+
+def _flatten_outputs(res):
+    """STN return values (tensor, list/tuple of tensors, nested) -> flat list of tensors in traversal order."""
+    if torch.is_tensor(res):
+        return [res]
+    out = []
+    for r in res:
+        out += _flatten_outputs(r)
+    return out
+
+
+def gen_stn_options(ref_models):
+    """Orchestration options of the STN API: iterated similarity, composed similarity+flow with
+    alpha / output_resolution / return_sim / return_intermediates, multi-head cartesian policy and unfold --
+    reference spatial_transformer.py:78-139, :523-615 on CPU with seeded weights."""
+    from oracle import opset
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from models.spatial_transformers.spatial_transformer import get_stn
+    out = {}
+    for i, (name, transforms, heads, kw) in enumerate(STN_OPTION_CASES):
+        gen = torch.Generator().manual_seed(7000 + i)
+        stn = get_stn(list(transforms), flow_size=64, supersize=64, channel_multiplier=0.25, num_heads=heads).eval()
+        opset.fill_parameters(stn, 31 + i, gain=0.3)
+        x = torch.randn(2 if "alpha" in kw else 1, 3, 64, 64, generator=gen)
+        with torch.no_grad():
+            res = stn(x, **stn_option_kwargs(kw))
+        out["opt_" + name + ".x"] = x
+        for j, t in enumerate(_flatten_outputs(res)):
+            out["opt_%s.out%d" % (name, j)] = t
+    _save("stn_options", **out)
+
+
+EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual, gen_points, gen_stn_options]
 
 if __name__ == "__main__":
     main()

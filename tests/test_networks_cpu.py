@@ -119,3 +119,31 @@ def test_point_transfer_matches_reference_fixture(transforms):
         assert_close(congealed, ref, rtol=1e-5, what="congealed points")
     assert_close(back, blob[tag + ".uncongealed"], rtol=1e-5, what="uncongealed points")
     assert_close(moved, blob[tag + ".transferred"], rtol=1e-5, what="transferred points")
+
+
+def _flat(res):
+    if torch.is_tensor(res):
+        return [res]
+    out = []
+    for r in res:
+        out += _flat(r)
+    return out
+
+
+def test_stn_orchestration_options_match_reference_fixture():
+    """iterated similarity, composed STN with alpha / output_resolution / return_sim /
+    return_intermediates, multi-head cartesian policy and unfold -- same calls as oracle/make_golden.py made on the
+    reference (spatial_transformer.py:78-139, :523-615)."""
+    from gangealing_b200.stn import get_stn
+    from oracle.make_golden import STN_OPTION_CASES, stn_option_kwargs
+    blob = load_golden("stn_options")
+    for i, (name, transforms, heads, kw) in enumerate(STN_OPTION_CASES):
+        stn = get_stn(list(transforms), flow_size=64, supersize=64, channel_multiplier=0.25, num_heads=heads, ops=CPU).eval()
+        opset.fill_parameters(stn, 31 + i, gain=0.3)
+        with torch.no_grad():
+            res = _flat(stn(blob["opt_" + name + ".x"], **stn_option_kwargs(kw)))
+        expected = [blob[k] for k in sorted((k for k in blob if k.startswith("opt_" + name + ".out")),
+                                            key=lambda k: int(k.rsplit("out", 1)[1]))]
+        assert len(res) == len(expected), name
+        for j, (a, e) in enumerate(zip(res, expected)):
+            assert_close(a, e, rtol=2e-4, what="%s output %d" % (name, j))
