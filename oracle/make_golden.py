@@ -416,7 +416,24 @@ def gen_stn_options(ref_models):
     _save("stn_options", **out)
 
 
-EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual, gen_points, gen_stn_options]
+def gen_perceptual_loss(ref_models):
+    """The whole perceptual loss as the training script builds it (lpips.py:13-17: LPIPS(net='vgg', lpips=False,
+    pnet_rand=True) / 18) with seeded VGG16 weights: value and input gradients on small images.  The weights are
+    regenerated from the seed by the test (oracle.opset.fill_convs_in_order), only inputs/outputs are stored."""
+    import models.losses.lpips as L
+    from oracle import opset
+    net = L.LPIPS(net="vgg", lpips=False, pnet_rand=True, verbose=False)
+    opset.fill_convs_in_order(net, 4242)
+    g = torch.Generator().manual_seed(4243)
+    in0 = (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).requires_grad_(True)
+    in1 = (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).requires_grad_(True)
+    val = net(in0, in1) / 18.0
+    g0, g1 = torch.autograd.grad(val.sum(), [in0, in1])
+    _save("perceptual_loss", in0=in0.detach(), in1=in1.detach(), val=val.detach(), g0=g0, g1=g1)
+
+
+EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual, gen_points, gen_stn_options,
+                    gen_perceptual_loss]
 
 if __name__ == "__main__":
     main()

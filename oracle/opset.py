@@ -106,3 +106,17 @@ def fill_parameters(module, seed=0, gain=1.0):
                 vals = vals * 0.1
             t.copy_(vals.to(t.dtype))
     return module
+
+
+def fill_convs_in_order(module, seed):
+    """He-scaled seeded weights for every Conv2d of `module`, in construction order -- the same values for two
+    implementations of the same convolution stack whose parameter NAMES differ (reference LPIPS vs this repo's)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in module.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                fan_in = m.in_channels * m.kernel_size[0] * m.kernel_size[1]
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)
+                if m.bias is not None:
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+    return module

@@ -77,3 +77,20 @@ def test_fused_kernels_match_oracle(shape):
     # symmetry and identity: d(a, b) == d(b, a), d(a, a) == 0 -- size-independent properties
     assert_close(feature_distance(y, x), r, rtol=1e-6)
     assert float(feature_distance(x, x).abs().max()) < 1e-12   # a*ia - b*ib contracts to an fma: one rounding residual
+
+
+def test_whole_perceptual_loss_matches_the_reference_lpips_fixture():
+    """PerceptualLoss (this repo's mirror of LPIPS(net='vgg', lpips=False, pnet_rand=True)/18, lpips.py:13-17) against
+    the reference class run with the same seeded VGG16 weights: scaling layer, slice boundaries, distance, gradients."""
+    from gangealing_b200.training.perceptual import PerceptualLoss
+    from oracle import opset
+    blob = load_golden("perceptual_loss")
+    loss = opset.fill_convs_in_order(PerceptualLoss(), 4242)
+    in0 = blob["in0"].clone().requires_grad_(True)
+    in1 = blob["in1"].clone().requires_grad_(True)
+    val = loss(in0, in1)
+    assert val.shape == blob["val"].shape
+    assert_close(val, blob["val"], rtol=1e-5, what="perceptual distance")
+    g0, g1 = torch.autograd.grad(val.sum(), [in0, in1])
+    assert_close(g0, blob["g0"], rtol=1e-4, what="d/d in0")
+    assert_close(g1, blob["g1"], rtol=1e-4, what="d/d in1")
