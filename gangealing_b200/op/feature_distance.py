@@ -3,8 +3,9 @@ difference, optional per-channel weights, spatial mean.
 
 reference: models/losses/lpips.py:26-28 (`normalize_tensor`), :193-205 (difference, `lins` / channel sum), :226
 (`spatial_average`).  `feature_distance(f0, f1, weight=None)` returns (N, 1, 1, 1) like the reference's per-layer `res`.
-CUDA channels-last fp32 inputs take the fused kernels (forward: one read of both maps; backward: one read + one write
-of both); anything else (NCHW, CPU tensors of the oracle legs) evaluates the same formula with tensor ops."""
+CUDA tensors only (like every op here: no CPU path in the product).  Channels-last fp32 inputs take the fused kernels
+(forward: one read of both maps; backward: one read + one write of both); other CUDA layouts / dtypes evaluate the same
+formula with ATen ops on the device."""
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -63,6 +64,7 @@ class _FeatureDistance(Function):
 
 def feature_distance(f0, f1, weight=None, eps=1e-10):
     """mean_hw sum_c w_c (f0/|f0| - f1/|f1|)^2 -> (N, 1, 1, 1).  `weight`: (C,) non-trainable `lins` weights or None."""
+    _lib.require_cuda(f0, f1, weight)
     if _supported(f0, f1) and (weight is None or not weight.requires_grad):
         return _FeatureDistance.apply(f0, f1, weight, float(eps))
     return _composite(f0, f1, weight, eps)

@@ -18,6 +18,7 @@ def cuda_ops():
         from .stn import flow as _flow
         from .stn import sampling as _smp
         from .splat2d import splat2d as _splat2d
+        from .op import feature_distance as _fd
         _cached = types.SimpleNamespace(
             name="sm_100a",
             upfirdn2d=_op.upfirdn2d,
@@ -34,5 +35,6 @@ def cuda_ops():
             bilinear_downsample=_smp.bilinear_downsample,
             flow_compose=_flow.flow_compose,
             splat2d=_splat2d,
+            feature_distance=_fd.feature_distance,
         )
     return _cached

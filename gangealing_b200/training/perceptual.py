@@ -6,7 +6,6 @@ for the SimCLR checkpoint, exactly as BASELINE.md section 3 prescribes for the o
 import torch
 import torch.nn as nn
 
-from ..op.feature_distance import feature_distance
 
 _VGG16_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _SLICE_ENDS = (4, 9, 16, 23, 30)  # relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 in torchvision's layer numbering
@@ -43,8 +42,9 @@ class VGG16Slices(nn.Module):
 class PerceptualLoss(nn.Module):
     """d(x, y) = sum_layers mean_hw sum_c (f/|f| - g/|g|)^2 on ImageNet-style rescaled inputs, / 18."""
 
-    def __init__(self, divisor=18.0):
+    def __init__(self, divisor=18.0, ops=None):
         super().__init__()
+        self.ops = ops        # None = the sm_100a op set (resolved lazily); tests / CPU legs inject the oracle's
         self.register_buffer("shift", torch.tensor([-.030, -.088, -.188])[None, :, None, None])
         self.register_buffer("scale", torch.tensor([.458, .448, .450])[None, :, None, None])
         self.net = VGG16Slices()
@@ -61,18 +61,22 @@ class PerceptualLoss(nn.Module):
         cl = torch.channels_last if in0.is_cuda else torch.contiguous_format
         f0 = self.net(((in0 - self.shift) / self.scale).contiguous(memory_format=cl))
         f1 = self.net(((in1 - self.shift) / self.scale).contiguous(memory_format=cl))
+        ops = self.ops
+        if ops is None:
+            from ..opset import cuda_ops
+            ops = cuda_ops()
         val = 0
         for a, b in zip(f0, f1):
             # normalise, difference, channel sum and spatial mean in one pass over both maps (csrc/lpips.cu) on
             # channels-last CUDA features; the same formula with tensor ops elsewhere (lpips.py:193-205, :226)
-            val = val + feature_distance(a, b)
+            val = val + ops.feature_distance(a, b)
         return val / self.divisor
 
 
-def get_perceptual_loss(device, seed=0):
+def get_perceptual_loss(device, seed=0, ops=None):
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)
-    loss = PerceptualLoss()
+    loss = PerceptualLoss(ops=ops)
     torch.random.set_rng_state(g)
     loss = loss.to(device)
     if torch.device(device).type == "cuda":

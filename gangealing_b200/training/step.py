@@ -83,7 +83,7 @@ class Trainer:
                     m.channels_last = True
         self.ll = DirectionInterpolator(None, cfg.ndirs, cfg.inject, self.generator.n_latent, num_heads=cfg.num_heads,
                                         dim_latent=cfg.dim_latent).to(device)
-        self.loss_fn = get_perceptual_loss(device, seed=cfg.seed + 1)
+        self.loss_fn = get_perceptual_loss(device, seed=cfg.seed + 1, ops=ops)
         self.resize_fake2stn = (BilinearDownsample(cfg.gen_size // cfg.flow_size, 3, ops=ops).to(device)
                                 if cfg.gen_size > cfg.flow_size else nn.Sequential())
         requires_grad(self.generator, False)

@@ -7,6 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from . import flow as _flow
+from . import perceptual as _perc
 from . import sampling as _smp
 from . import splat as _splat
 from . import stylegan2_ops as _so
@@ -84,6 +85,7 @@ def cpu_ops():
             bilinear_downsample=_bilinear_downsample,
             flow_compose=_flow_compose,
             splat2d=_splat.splat2d_ref,
+            feature_distance=_perc.feature_distance_ref,
         )
     return _ops
 

@@ -29,12 +29,14 @@ def test_oracle_matches_reference_fixture():
         assert_close(gb, g1, rtol=1e-6, what=name + " g1")
 
 
-def test_python_fallback_is_the_same_formula_on_cpu():
-    from gangealing_b200.op.feature_distance import feature_distance
+def test_device_side_composite_is_the_same_formula_and_the_op_refuses_cpu_tensors():
+    from gangealing_b200.op.feature_distance import _composite, feature_distance
     g = torch.Generator().manual_seed(2)
     a, b = torch.rand(2, 12, 5, 5, generator=g), torch.rand(2, 12, 5, 5, generator=g)
     w = torch.rand(12, generator=g)
-    assert_close(feature_distance(a, b, w), feature_distance_ref(a, b, w), rtol=1e-6)
+    assert_close(_composite(a, b, w, 1e-10), feature_distance_ref(a, b, w), rtol=1e-6)   # the unsupported-layout route
+    with pytest.raises(RuntimeError):
+        feature_distance(a, b, w)                                                         # no CPU path in the product
 
 
 @pytest.mark.gpu
@@ -85,7 +87,7 @@ def test_whole_perceptual_loss_matches_the_reference_lpips_fixture():
     from gangealing_b200.training.perceptual import PerceptualLoss
     from oracle import opset
     blob = load_golden("perceptual_loss")
-    loss = opset.fill_convs_in_order(PerceptualLoss(), 4242)
+    loss = opset.fill_convs_in_order(PerceptualLoss(ops=opset.cpu_ops()), 4242)
     in0 = blob["in0"].clone().requires_grad_(True)
     in1 = blob["in1"].clone().requires_grad_(True)
     val = loss(in0, in1)
