@@ -7,7 +7,6 @@ functions fall straight through to cuDNN via torch.nn.functional; that library c
 """
 import contextlib
 
-import torch
 from torch.nn import functional as F
 
 enabled = False

@@ -6,7 +6,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ..opset import cuda_ops
 from ..stylegan2.networks import ConvLayer, EqualLinear, ResBlock, channel_table

@@ -5,7 +5,6 @@ Trainer.step() = gangealing_loss forward (G x2, STN, perceptual) -> TV / identit
 times for the "train images/sec at 256^2" metric.
 """
 import dataclasses
-import math
 
 import torch
 from torch import nn, optim

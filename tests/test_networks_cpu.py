@@ -1,6 +1,5 @@
 """CPU: the host-side networks (run on the oracle op set) against (a) the reference's own modules when the
 checkout is present in this container and (b) fixtures generated from them -- state-dict compatibility included."""
-import os
 
 import pytest
 import torch

@@ -1,5 +1,4 @@
 """CPU: the oracle restatement reproduces the fixtures generated from the reference (oracle/make_golden.py)."""
-import pytest
 import torch
 
 from conftest import assert_close, golden_cases, load_golden

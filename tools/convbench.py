@@ -1,6 +1,6 @@
 """Grouped (per-sample weights, reference formulation) vs dense (shared weights, modulate activations) convolution
 timing at the generator's layer shapes; fwd and fwd+bwd.  Decides how ModulatedConv2d should call cuDNN."""
-import sys, torch, torch.nn.functional as F
+import torch, torch.nn.functional as F
 torch.backends.cudnn.benchmark = True
 dev = "cuda"
 def t(fn, it=10):
