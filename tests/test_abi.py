@@ -46,3 +46,31 @@ def test_ops_refuse_cpu_tensors():
         upfirdn2d(torch.zeros(1, 1, 8, 8), torch.ones(4, 4))
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         fused_leaky_relu(torch.zeros(1, 2, 4, 4), torch.zeros(2))
+
+
+def test_argument_validation_of_the_channels_last_and_loss_entry_points():
+    """Host-side validation runs before any device work: unsupported shapes come back as status codes + messages."""
+    dll = _lib.load()
+    one = 1  # any non-null pointer value: validation must reject these calls before dereferencing anything
+    # perceptual front end: C must be a power of two below 128 or a multiple of 128
+    assert dll.gg_feature_distance_forward(one, one, one, one, None, 2, 24, 16, 1e-10, None) == -2
+    assert b"feature_distance" in dll.gg_last_error()
+    assert dll.gg_feature_distance_forward(one, one, one, one, None, 2, 192, 16, 1e-10, None) == -2
+    assert dll.gg_feature_distance_backward(one, one, one, one, one, None, -1, 64, 16, 1e-10, None) == -1
+    assert dll.gg_feature_distance_workspace(0, 64, 16) == 0
+    # BilinearDownsample: stride range, reflection needs a plane larger than stride/2
+    assert dll.gg_tent_downsample_forward(one, one, one, one, 1, 3, 8, 8, 0, None) == -2
+    assert dll.gg_tent_downsample_forward(one, one, one, one, 1, 3, 8, 8, 17, None) == -2
+    assert dll.gg_tent_downsample_forward(one, one, one, one, 1, 3, 2, 8, 4, None) == -1
+    assert dll.gg_tent_downsample_backward(one, one, one, one, 1, 3, 8, 8, 0, None) == -2
+    assert dll.gg_tent_downsample_forward(None, None, None, None, 0, 3, 8, 8, 2, None) == 0      # empty batch: nothing to do
+    # to-RGB and the NHWC family: channel-count contracts
+    assert dll.gg_to_rgb_nhwc_forward(one, one, one, None, None, 1, 20, 16, None) == -2
+    assert dll.gg_to_rgb_nhwc_backward(one, one, one, one, one, one, 1, 6, 16, None) == -2
+    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, one, 1, 6, 16, None) == -2
+    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, None, 1, 8, 16, None) == -1      # null scale
+    assert dll.gg_bias_act_backward_nhwc(one, None, None, one, None, 0.2, 1.0, 1, 8, 16, None) == -1  # null saved output
+    assert dll.gg_noise_bias_act_nhwc(one, one, None, None, None, None, 0.2, 1.0, 1, 6, 16, None) == -2
+    assert dll.gg_blur_nhwc(one, one, one, None, None, None, None, 1, 20, 8, 8, 4, 4, 1, 1, 1, 1, 1, 0, 1, 0.0, 1.0, None) == -2
+    assert dll.gg_blur_nhwc(one, one, one, None, None, None, None, 1, 32, 8, 8, 5, 5, 1, 1, 1, 1, 1, 0, 1, 0.0, 1.0, None) == -2
+    assert dll.gg_blur_nhwc(one, one, one, None, None, None, None, 1, 32, 8, 8, 4, 4, 1, 1, 1, 1, 1, 0, 2, 0.0, 1.0, None) == -2
