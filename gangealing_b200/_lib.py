@@ -102,9 +102,16 @@ def dtype_code(t):
 def require_cuda(*tensors):
     """Mirror of the reference's CHECK_CUDA (models/stylegan2/op/upfirdn2d.cpp:8): CUDA tensors only."""
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("gangealing_b200 ops run on CUDA tensors only (got a %s tensor); "
                                "the CPU restatement lives in oracle/ and is test infrastructure" % t.device.type)
+        if t.device.index != torch.cuda.current_device():
+            # the C ABI launches on the CURRENT device's stream (one process per GPU, like the reference's torchrun
+            # recipe): refuse a tensor of another device instead of launching on the wrong one
+            raise RuntimeError("gangealing_b200: tensor lives on %s but the current device is cuda:%d; wrap the call in "
+                               "`with torch.cuda.device(tensor.device):`" % (t.device, torch.cuda.current_device()))
 
 
 def ptr(t):
@@ -120,9 +127,12 @@ def is_nhwc(t):
 def tensor_cache(t):
     """Per-tensor-object memo, invalidated when the tensor is modified in place.  (Keyed on the Python object, not on
     data_ptr: a freed temporary's address can be handed to a different tensor.)"""
+    # the stamp also carries the storage address, device and dtype: `.data` writes (the reference's own
+    # accumulate(), weight surgery) and module.to(device) keep the Python object and its version counter
+    stamp = (t._version, t.data_ptr(), t.device, t.dtype)
     ent = getattr(t, "_gg_cache", None)
-    if ent is None or ent[0] != t._version:
-        ent = (t._version, {})
+    if ent is None or ent[0] != stamp:
+        ent = (stamp, {})
         try:
             t._gg_cache = ent
         except Exception:
@@ -159,6 +169,15 @@ def flipped_filter(kernel):
             fm["separable"] = memo["separable"]
         memo["flipped"] = f
     return f
+
+
+def invalidate(t):
+    """Drop the memo of a tensor that was rewritten through `.data` IN PLACE at the same address (which no stamp can see):
+    call it from weight-loading / conversion hooks."""
+    try:
+        t._gg_cache = None
+    except Exception:
+        pass
 
 
 def stream():

@@ -39,6 +39,20 @@ inline int cuda_fail(cudaError_t e, const char* what) {
 
 int sm_count();  // defined in api.cu
 
+// One-time per-DEVICE configuration guard (cudaFuncSetAttribute is a per-device attribute, so a process that drives a
+// second GPU must opt in there too).  Usage:  static DeviceOnce once;  if (once.needed()) { ...; once.done(); }
+struct DeviceOnce {
+  unsigned long long mask[2] = {0ull, 0ull};   // up to 128 device ordinals; benign race: configuring twice is harmless
+  int dev = 0;
+  bool needed() {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return true;
+    return ((__atomic_load_n(&mask[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) == 0ull;
+  }
+  void done() {
+    if (dev >= 0 && dev < 128) __atomic_fetch_or(&mask[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
+  }
+};
+
 // ---------------------------------------------------------------- dtype traits (fp32 math)
 template <typename T> struct Cvt;
 template <> struct Cvt<float> {
@@ -99,9 +113,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+// Bounded: a transfer that never completes (a bad tensor map, a faulted copy) traps after ~2^28 polls instead of
+// hanging the GPU until the watchdog fires.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
+  uint32_t spins = 0;
   do {
+    if (++spins == (1u << 28)) __trap();
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"

@@ -319,15 +319,15 @@ int gg_modconv_demod(float* demod, const float* wsq, const float* style, float s
   while (tmem_cols < n_pad) tmem_cols <<= 1;
   const int na = (n_pad <= 32 && I >= 4 * kBlockK) ? 4 : ((n_pad <= 64 && I > kBlockK) ? 2 : 1);
   const size_t smem = static_cast<size_t>(na) * (2 * 128 + 2 * n_pad) * kBlockK * sizeof(float) + 1024;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(demod_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(demod_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(demod_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "modconv_demod smem opt-in");
-    configured = true;
+    configured.done();
   }
   auto st = static_cast<cudaStream_t>(stream);
   if (na == 4)

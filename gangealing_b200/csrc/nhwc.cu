@@ -745,8 +745,8 @@ int gg_blur_nhwc(float* out, const float* in, const float* kernel, const float* 
   const dim3 grid(static_cast<unsigned>(xblocks * (C / kCB)), static_cast<unsigned>((out_h + seg_rows - 1) / seg_rows),
                   static_cast<unsigned>(N));
   const size_t smem = static_cast<size_t>(kNS) * kStageFloats * sizeof(float);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaSuccess;
     const void* kernels[4] = {reinterpret_cast<const void*>(blur_nhwc_kernel<true, true>),
                               reinterpret_cast<const void*>(blur_nhwc_kernel<true, false>),
@@ -755,7 +755,7 @@ int gg_blur_nhwc(float* out, const float* in, const float* kernel, const float* 
     for (int i = 0; i < 4 && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_fail(e, "blur_nhwc smem opt-in");
-    configured = true;
+    configured.done();
   }
   auto st = static_cast<cudaStream_t>(stream);
 #define GG_BLUR(F_, S_) blur_nhwc_kernel<F_, S_><<<grid, kT, smem, st>>>(out, tmap, kernel, kernel_h, kernel_w, noise, noise_weight, bias, row_scale, p)

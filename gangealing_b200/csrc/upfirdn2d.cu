@@ -683,12 +683,12 @@ template <typename T, int IW4, bool FUSED>
 int launch_band_t(const BandPlan& pl, void* out, const void* in, const float* filt, int kh, int kw, const void* noise,
                   const float* nw, const float* bias, const float* row_scale, cudaStream_t st) {
   auto kern = fir4_band_kernel<T, IW4, FUSED>;
-  static thread_local bool configured = false;  // per instantiation, per thread
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(200 * 1024));
     if (e != cudaSuccess) return cuda_fail(e, "fir4_band smem opt-in");
-    configured = true;
+    configured.done();
   }
   kern<<<pl.grid, kBandThreads, pl.smem_bytes, st>>>(
       static_cast<T*>(out), static_cast<const T*>(in), filt, kh, kw, static_cast<const T*>(noise), nw, bias,

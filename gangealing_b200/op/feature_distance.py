@@ -3,9 +3,10 @@ difference, optional per-channel weights, spatial mean.
 
 reference: models/losses/lpips.py:26-28 (`normalize_tensor`), :193-205 (difference, `lins` / channel sum), :226
 (`spatial_average`).  `feature_distance(f0, f1, weight=None)` returns (N, 1, 1, 1) like the reference's per-layer `res`.
-CUDA tensors only (like every op here: no CPU path in the product).  Channels-last fp32 inputs take the fused kernels
-(forward: one read of both maps; backward: one read + one write of both); other CUDA layouts / dtypes evaluate the same
-formula with ATen ops on the device."""
+CUDA tensors only (like every op here: no CPU path in the product).  The fused kernels want channels-last fp32 feature
+maps (forward: one read of both maps; backward: one read + one write of both): other layouts / float dtypes are
+converted to that form first (one copy), anything the kernel cannot take (trainable `lins` weights, odd channel counts)
+raises -- there is no eager tensor-op route."""
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -13,21 +14,20 @@ from torch.autograd.function import once_differentiable
 from .. import _lib
 
 
-def _composite(f0, f1, weight, eps):
-    def unit(f):
-        return f / (torch.sqrt(torch.sum(f ** 2, dim=1, keepdim=True)) + eps)
-    d = (unit(f0) - unit(f1)) ** 2
-    if weight is not None:
-        d = d * weight.reshape(1, -1, 1, 1)
-    return d.sum(dim=1, keepdim=True).mean([2, 3], keepdim=True)
-
-
-def _supported(f0, f1):
-    c = f0.shape[1]
+def _channels_ok(c):
     c4 = c // 4
-    ok_c = c % 4 == 0 and c <= 1024 and ((c4 < 32 and c4 & (c4 - 1) == 0) or (c4 >= 32 and c4 % 32 == 0))
-    return (f0.is_cuda and f0.dtype == torch.float32 and f1.dtype == torch.float32 and f0.shape == f1.shape and ok_c
-            and f0.dim() == 4 and _lib.is_nhwc(f0) and _lib.is_nhwc(f1))
+    return c % 4 == 0 and c <= 1024 and ((c4 < 32 and c4 & (c4 - 1) == 0) or (c4 >= 32 and c4 % 32 == 0))
+
+
+def _as_kernel_input(f):
+    """channels-last fp32 view/copy of a (N, C, H, W) feature map (autograd-tracked conversion when one is needed)."""
+    if f.dtype != torch.float32:
+        f = f.float()
+    if f.shape[1] > 1 and f.shape[2] * f.shape[3] > 1:
+        f = f.contiguous(memory_format=torch.channels_last)
+    else:   # degenerate shapes are both layouts at once: any dense buffer is (N, HW, C)
+        f = f.contiguous()
+    return f
 
 
 class _FeatureDistance(Function):
@@ -65,6 +65,13 @@ class _FeatureDistance(Function):
 def feature_distance(f0, f1, weight=None, eps=1e-10):
     """mean_hw sum_c w_c (f0/|f0| - f1/|f1|)^2 -> (N, 1, 1, 1).  `weight`: (C,) non-trainable `lins` weights or None."""
     _lib.require_cuda(f0, f1, weight)
-    if _supported(f0, f1) and (weight is None or not weight.requires_grad):
-        return _FeatureDistance.apply(f0, f1, weight, float(eps))
-    return _composite(f0, f1, weight, eps)
+    if f0.dim() != 4 or f0.shape != f1.shape:
+        raise RuntimeError("feature_distance: expected two (N, C, H, W) maps of one shape, got %s and %s" %
+                           (tuple(f0.shape), tuple(f1.shape)))
+    if not _channels_ok(f0.shape[1]):
+        raise RuntimeError("feature_distance: C=%d is not supported by the fused kernel (C %% 4 == 0, C <= 1024, C/4 a power "
+                           "of two below 32 or a multiple of 32)" % f0.shape[1])
+    if weight is not None and weight.requires_grad:
+        raise RuntimeError("feature_distance: trainable `lins` weights are not supported (the reference trains with "
+                           "frozen LPIPS weights, lpips.py:13-22)")
+    return _FeatureDistance.apply(_as_kernel_input(f0), _as_kernel_input(f1), weight, float(eps))

@@ -34,6 +34,14 @@ class _FlowCompose(Function):
             raise RuntimeError("flow_compose: identity_flow must be (1, %d, %d, 2)" % (s * h, s * w))
         if base_c is not None and base_c.numel() != n * 6:
             raise RuntimeError("flow_compose: base_warp must be (N, 2, 3)")
+        if alpha_c is not None:
+            # the reference broadcasts `identity_flow.lerp(flow, alpha[:, None, None, None])` (warping_heads.py:243-244):
+            # a 1-element alpha serves any batch; the kernel reads alpha[n] for every n, so expand it here
+            alpha_c = alpha_c.reshape(-1)
+            if alpha_c.numel() == 1:
+                alpha_c = alpha_c.expand(n).contiguous()
+            elif alpha_c.numel() != n:
+                raise RuntimeError("flow_compose: alpha must have 1 or N=%d elements, got %d" % (n, alpha_c.numel()))
         delta = torch.empty((n, s * h, s * w, 2), dtype=torch.float32, device=low.device)
         flow = torch.empty_like(delta) if want_flow else None
         rc = _lib.load().gg_flow_compose_forward(delta.data_ptr(), _lib.ptr(flow), low_c.data_ptr(), mask_c.data_ptr(),

@@ -145,19 +145,19 @@ class _TentDownsample(Function):
 
 def bilinear_downsample(input, stride, kernel_horz, kernel_vert):
     """Functional form of BilinearDownsample.forward (reference antialiased_sampling.py:254-256): reflect-pad +
-    separable tent filter with stride.  fp32 images take the single-kernel path; other dtypes the two depthwise
-    convolutions of the reference."""
-    channels = input.shape[1]
-    if input.dtype == torch.float32 and input.dim() == 4 and 2 * stride <= 32:
-        taps = 2 * stride
-        th = kernel_horz.reshape(channels, taps).float().contiguous()
-        tv = kernel_vert.reshape(channels, taps).float().contiguous()
-        return _TentDownsample.apply(input, th, tv, int(stride))
+    separable tent filter with stride, as ONE gather kernel (csrc/resample.cu).  Half-precision images are filtered in
+    fp32 and cast back; there is no ATen route."""
     _lib.require_cuda(input)
-    pad = int(stride / 2)
-    x = F.pad(input, (pad, pad, pad, pad), mode="reflect")
-    rows = F.conv2d(x, kernel_horz, stride=(1, stride), groups=channels)
-    return F.conv2d(rows, kernel_vert, stride=(stride, 1), groups=channels)
+    if input.dim() != 4 or 2 * stride > 32:
+        raise RuntimeError("bilinear_downsample: expected a (N, C, H, W) image and stride <= 16, got %s, stride %d" %
+                           (tuple(input.shape), stride))
+    channels = input.shape[1]
+    taps = 2 * stride
+    th = kernel_horz.reshape(channels, taps).float().contiguous()
+    tv = kernel_vert.reshape(channels, taps).float().contiguous()
+    if input.dtype == torch.float32:
+        return _TentDownsample.apply(input, th, tv, int(stride))
+    return _TentDownsample.apply(input.float(), th, tv, int(stride)).to(input.dtype)
 
 
 def grid_sample_bilinear(inputs, grid, padding_mode="border"):

@@ -52,11 +52,11 @@ def assign_fake_images_to_clusters(generator, stn, ll, loss_fn, resize_fake2stn,
 
 
 def gangealing_cluster_loss(generator, stn, ll, loss_fn, resize_fake2stn, psi, batch, dim_latent, freeze_ll, num_heads,
-                            flips, device, sample_from_full_res=True, **stn_kwargs):
+                            flips, device, sample_from_full_res=True, z=None, **stn_kwargs):
     """Clustering reconstruction loss: only the assigned head's flow is regularised (reference loss.py:78-92)."""
     assignments, _, delta_flow, _, _, _ = assign_fake_images_to_clusters(
         generator, stn, ll, loss_fn, resize_fake2stn, psi, batch, dim_latent, freeze_ll, num_heads, flips, device,
-        sample_from_full_res, z=None, **stn_kwargs)
+        sample_from_full_res, z=z, **stn_kwargs)
     hw2 = delta_flow.size()[1:]
     if flips:
         delta_flow = delta_flow.view(2, batch, num_heads, *hw2).permute(1, 0, 2, 3, 4, 5).reshape(batch, 2 * num_heads, *hw2)

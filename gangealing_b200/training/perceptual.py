@@ -1,14 +1,22 @@
-"""Perceptual distance on VGG-16 features -- the `LPIPS(net='vgg', lpips=False, pnet_rand=True)` baseline the
-reference's 'vgg_ssl' loss builds (models/losses/lpips.py:13-17, :181-223; backbone lpips_backbones.py:98-140),
-divided by 18 like the reference.  OUT OF SCOPE for hand-written kernels (plain cuDNN convs);
-it exists so the training step is complete.  No weights are downloaded: random (seeded) initialisation stands in
-for the SimCLR checkpoint, exactly as BASELINE.md section 3 prescribes for the offline benchmark."""
+"""Perceptual distance on VGG-16 features -- host-side mirror of the reference's `LPIPS` (models/losses/lpips.py:125-231)
+in the two configurations its training script builds (lpips.py:13-22):
+
+  'vgg_ssl' : LPIPS(net='vgg', lpips=False, pnet_rand=True, pretrained_weights=simclr_vgg_phase150.pt) / 18
+  'lpips'   : LPIPS(net='vgg')  -- the linearly calibrated metric (`lin0..lin4`, 1x1 convs without bias)
+
+The module tree and state-dict keys are the reference's (`scaling_layer.{shift,scale}`, `net.slice{k}.{torchvision index}.*`,
+`lin{k}.model.1.weight`), so `load_state_dict` of a reference LPIPS checkpoint works, and `pretrained_weights=` loads a
+`torchvision.models.vgg16().features` state dict strictly, exactly like lpips_backbones.py:103-105.  The VGG convolutions
+stay cuDNN; the front end (normalise / difference / weights / spatial mean) is this package's fused
+kernel (csrc/lpips.cu).  Offline benchmarks use seeded random VGG weights.
+"""
 import torch
 import torch.nn as nn
 
 
 _VGG16_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _SLICE_ENDS = (4, 9, 16, 23, 30)  # relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 in torchvision's layer numbering
+_CHNS = (64, 128, 256, 512, 512)
 
 
 def _vgg16_features():
@@ -23,60 +31,129 @@ def _vgg16_features():
 
 
 class VGG16Slices(nn.Module):
+    """`slice1..slice5`, each an nn.Sequential whose children carry torchvision's `features` indices
+    (reference lpips_backbones.py:106-121)."""
+
     def __init__(self):
         super().__init__()
         feats = _vgg16_features()
         starts = (0,) + _SLICE_ENDS[:-1]
-        self.slices = nn.ModuleList([nn.Sequential(*feats[a:b]) for a, b in zip(starts, _SLICE_ENDS)])
+        for k, (a, b) in enumerate(zip(starts, _SLICE_ENDS), 1):
+            seq = nn.Sequential()
+            for idx in range(a, b):
+                seq.add_module(str(idx), feats[idx])
+            setattr(self, "slice%d" % k, seq)
+        self.N_slices = 5
         for p in self.parameters():
             p.requires_grad = False
 
+    def slices(self):
+        return [getattr(self, "slice%d" % k) for k in range(1, self.N_slices + 1)]
+
+    def load_features_state_dict(self, state_dict, strict=True):
+        """Load a `torchvision.models.vgg16().features` state dict ('0.weight', '2.bias', ...), strictly by default."""
+        own = {}
+        for k, seq in enumerate(self.slices(), 1):
+            for idx, layer in seq.named_children():
+                for name, _ in layer.named_parameters():
+                    own["%s.%s" % (idx, name)] = "slice%d.%s.%s" % (k, idx, name)
+        unexpected = [k for k in state_dict if k not in own]
+        if strict and unexpected:
+            raise RuntimeError("unexpected VGG16 feature keys (the reference slices stop at relu5_3): %s" % unexpected[:4])
+        return self.load_state_dict({own[k]: v for k, v in state_dict.items() if k in own}, strict=strict)
+
     def forward(self, x):
         outs = []
-        for s in self.slices:
+        for s in self.slices():
             x = s(x)
             outs.append(x)
         return outs
 
 
-class PerceptualLoss(nn.Module):
-    """d(x, y) = sum_layers mean_hw sum_c (f/|f| - g/|g|)^2 on ImageNet-style rescaled inputs, / 18."""
-
-    def __init__(self, divisor=18.0, ops=None):
+class ScalingLayer(nn.Module):
+    def __init__(self):
         super().__init__()
-        self.ops = ops        # None = the sm_100a op set (resolved lazily); tests / CPU legs inject the oracle's
         self.register_buffer("shift", torch.tensor([-.030, -.088, -.188])[None, :, None, None])
         self.register_buffer("scale", torch.tensor([.458, .448, .450])[None, :, None, None])
+
+    def forward(self, inp):
+        return (inp - self.shift) / self.scale
+
+
+class NetLinLayer(nn.Module):
+    """A 1x1 convolution without bias (reference lpips.py:236-245); with dropout the conv is `model.1`."""
+
+    def __init__(self, chn_in, chn_out=1, use_dropout=False):
+        super().__init__()
+        layers = [nn.Dropout()] if use_dropout else []
+        layers += [nn.Conv2d(chn_in, chn_out, 1, stride=1, padding=0, bias=False)]
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class PerceptualLoss(nn.Module):
+    """d(x, y) = sum_layers mean_hw sum_c w_c (f/|f| - g/|g|)^2 on ImageNet-style rescaled inputs, / divisor.
+    `lpips=False`: w = 1 (the 'vgg_ssl' baseline, divisor 18); `lpips=True`: w = the `lin{k}` weights (divisor 1)."""
+
+    def __init__(self, divisor=18.0, lpips=False, use_dropout=True, pretrained_weights=None, ops=None):
+        super().__init__()
+        self.ops = ops        # None = the sm_100a op set (resolved lazily); tests / CPU legs inject the oracle's
+        self.scaling_layer = ScalingLayer()
         self.net = VGG16Slices()
+        self.lpips = lpips
+        self.L = 5
+        if lpips:
+            for k, c in enumerate(_CHNS):
+                setattr(self, "lin%d" % k, NetLinLayer(c, use_dropout=use_dropout))
+            self.lins = nn.ModuleList([getattr(self, "lin%d" % k) for k in range(self.L)])
+        if pretrained_weights is not None:
+            sd = pretrained_weights if isinstance(pretrained_weights, dict) else \
+                torch.load(pretrained_weights, map_location="cpu")
+            self.net.load_features_state_dict(sd, strict=True)
         self.divisor = divisor
         self.eval()
+        for p in self.parameters():
+            p.requires_grad = False
 
-    @staticmethod
-    def _unit(feat, eps=1e-10):
-        return feat / (torch.sqrt(torch.sum(feat ** 2, dim=1, keepdim=True)) + eps)
+    # the registered-twice `lins` ModuleList mirrors the reference (lpips.py:162-168); keep its keys out of the state
+    # dict comparison the same way the reference's own checkpoints do (they hold both `lin0.*` and `lins.0.*`)
 
     def forward(self, in0, in1):
         # channels_last: cuDNN's tensor-core kernels are NHWC-native; NCHW inputs cost a layout conversion around
         # every convolution (22% of the step in profiles/r01_step_launches_b8_summary.txt)
         cl = torch.channels_last if in0.is_cuda else torch.contiguous_format
-        f0 = self.net(((in0 - self.shift) / self.scale).contiguous(memory_format=cl))
-        f1 = self.net(((in1 - self.shift) / self.scale).contiguous(memory_format=cl))
+        dt = self.net.slice1[0].weight.dtype   # bf16 when the Trainer runs BASELINE config 3
+        f0 = self.net(self.scaling_layer(in0).to(dt).contiguous(memory_format=cl))
+        f1 = self.net(self.scaling_layer(in1).to(dt).contiguous(memory_format=cl))
         ops = self.ops
         if ops is None:
             from ..opset import cuda_ops
             ops = cuda_ops()
         val = 0
-        for a, b in zip(f0, f1):
-            # normalise, difference, channel sum and spatial mean in one pass over both maps (csrc/lpips.cu) on
-            # channels-last CUDA features; the same formula with tensor ops elsewhere (lpips.py:193-205, :226)
-            val = val + ops.feature_distance(a, b)
+        for k, (a, b) in enumerate(zip(f0, f1)):
+            # normalise, difference, (weights,) channel sum and spatial mean in one pass over both maps (csrc/lpips.cu)
+            # on channels-last CUDA features; lpips.py:193-205, :226
+            w = self.lins[k].model[-1].weight.reshape(-1) if self.lpips else None
+            val = val + ops.feature_distance(a, b, w)
         return val / self.divisor
 
 
-def get_perceptual_loss(device, seed=0, ops=None):
+def get_perceptual_loss(device, seed=0, ops=None, kind="vgg_ssl", pretrained_weights=None, lpips_weights=None):
+    """kind='vgg_ssl' (default; reference lpips.py:14-17) or 'lpips' (lpips.py:18-20).  Without `pretrained_weights`
+    the VGG is seeded-random (offline benchmark); `lpips_weights`: a reference LPIPS state dict / path with `lin*` keys."""
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)
-    loss = PerceptualLoss(ops=ops)
+    if kind == "vgg_ssl":
+        loss = PerceptualLoss(divisor=18.0, lpips=False, pretrained_weights=pretrained_weights, ops=ops)
+    elif kind == "lpips":
+        loss = PerceptualLoss(divisor=1.0, lpips=True, pretrained_weights=pretrained_weights, ops=ops)
+        if lpips_weights is not None:
+            sd = lpips_weights if isinstance(lpips_weights, dict) else torch.load(lpips_weights, map_location="cpu")
+            loss.load_state_dict(sd, strict=False)
+    else:
+        raise NotImplementedError(kind)
     torch.random.set_rng_state(g)
     loss = loss.to(device)
     if torch.device(device).type == "cuda":

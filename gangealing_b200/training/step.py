@@ -107,11 +107,16 @@ class Trainer:
             else:
                 wrap()
         fused = torch.device(device).type == "cuda"
-        # capturable: the optimiser state lives on the device so a whole iteration can be replayed as a CUDA graph
-        self.t_optim = optim.Adam(self.t_module.parameters(), lr=cfg.stn_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused,
-                                  capturable=fused)
-        self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=cfg.ll_lr, betas=(0.9, 0.999), eps=1e-8, fused=fused,
-                                   capturable=fused)
+        # capturable: the optimiser state AND the learning rates live on the device, psi too, so ONE captured CUDA graph
+        # serves the whole schedule (psi 1 -> 0, cyclic lr: reference train.py:89-96,129-132); `step(psi=, lr=, ll_lr=)`
+        # copies new values into these scalars before the replay
+        self.psi_t = torch.tensor(float(cfg.psi), device=device)
+        self.stn_lr_t = torch.tensor(float(cfg.stn_lr), device=device) if fused else None
+        self.ll_lr_t = torch.tensor(float(cfg.ll_lr), device=device) if fused else None
+        self.t_optim = optim.Adam(self.t_module.parameters(), lr=self.stn_lr_t if fused else cfg.stn_lr, betas=(0.9, 0.999),
+                                  eps=1e-8, fused=fused, capturable=fused)
+        self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=self.ll_lr_t if fused else cfg.ll_lr, betas=(0.9, 0.999),
+                                   eps=1e-8, fused=fused, capturable=fused)
         self._graph = None
         self.accum = 0.5 ** (32 / (10 * 1000))
         self.zero = torch.tensor(0.0, device=device)
@@ -122,21 +127,45 @@ class Trainer:
         cfg = self.cfg
         if cfg.num_heads > 1 or cfg.flips:
             perceptual, delta_flow = gangealing_cluster_loss(
-                self.generator, self.stn, self.ll, self.loss_fn, self.resize_fake2stn, cfg.psi, cfg.batch, cfg.dim_latent,
-                cfg.freeze_ll, cfg.num_heads, cfg.flips, self.device, sample_from_full_res=cfg.sample_from_full_res,
+                self.generator, self.stn, self.ll, self.loss_fn, self.resize_fake2stn, self.psi_t, cfg.batch, cfg.dim_latent,
+                cfg.freeze_ll, cfg.num_heads, cfg.flips, self.device, sample_from_full_res=cfg.sample_from_full_res, z=z,
                 padding_mode=cfg.padding_mode)
         else:
             perceptual, delta_flow = gangealing_loss(
-                self.generator, self.stn, self.ll, self.loss_fn, self.resize_fake2stn, cfg.psi, cfg.batch, cfg.dim_latent,
+                self.generator, self.stn, self.ll, self.loss_fn, self.resize_fake2stn, self.psi_t, cfg.batch, cfg.dim_latent,
                 cfg.freeze_ll, self.device, sample_from_full_res=cfg.sample_from_full_res, z=z,
                 padding_mode=cfg.padding_mode)
         tv = total_variation_loss(delta_flow) if cfg.tv_weight > 0 else self.zero
         idt = flow_identity_loss(delta_flow) if cfg.flow_identity_weight > 0 else self.zero
         return {"p": perceptual, "tv": tv, "f": idt}
 
-    def step(self, z=None):
+    def set_schedule(self, psi=None, lr=None, ll_lr=None):
+        """Update the truncation psi and the two learning rates (plain floats or 0-dim tensors).  They live in device
+        scalars, so this works before AND after `capture()` -- the captured graph reads them at replay time."""
+        if psi is not None:
+            self.psi_t.fill_(psi) if not torch.is_tensor(psi) else self.psi_t.copy_(psi, non_blocking=True)
+        for value, scalar, optimiser in ((lr, self.stn_lr_t, self.t_optim), (ll_lr, self.ll_lr_t, self.ll_optim)):
+            if value is None:
+                continue
+            if scalar is not None:
+                scalar.fill_(value) if not torch.is_tensor(value) else scalar.copy_(value, non_blocking=True)
+            else:
+                for group in optimiser.param_groups:
+                    group["lr"] = float(value)
+
+    def set_iteration(self, i, **recipe):
+        """psi and learning rates of iteration `i` of the reference recipe (training/schedule.py:schedule_at)."""
+        from .schedule import schedule_at
+        s = schedule_at(i, self.cfg.stn_lr, self.cfg.ll_lr, **recipe)
+        self.set_schedule(psi=s["psi"], lr=s["stn_lr"], ll_lr=s["ll_lr"])
+        return s
+
+    def step(self, z=None, psi=None, lr=None, ll_lr=None):
         """-> dict of (rank-0 averaged) scalar loss tensors, still on the device (no host sync here).
-        After `capture()` the iteration is replayed from a CUDA graph (z, if given, is copied into its static input)."""
+        After `capture()` the iteration is replayed from a CUDA graph (z, if given, is copied into its static input;
+        psi / lr / ll_lr, if given, into the device scalars the graph reads)."""
+        if psi is not None or lr is not None or ll_lr is not None:
+            self.set_schedule(psi, lr, ll_lr)
         if self._graph is not None:
             if z is None:
                 self._static_z.normal_()

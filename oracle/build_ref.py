@@ -10,6 +10,14 @@ for sm_100a ("the kernel bar").  No reference source is c
                                     The reference's host wrapper splat_gpu.c includes <THC/THC.h>, which modern
                                     torch no longer ships, so it is not built; oracle/splat.py restates its
                                     clone / zeros / clamp / divide (splat_gpu.c:20-41).
+  refpy/                          : the reference's own Python networks (models/**, utils/{__init__,distributed,
+                                    download}.py) BYTE-COMPILED (py_compile, sourceless .pyc -- a compiled output
+                                    like the .so files, no source text enters the repo) so that the UNMODIFIED
+                                    reference Generator / get_stn / gangealing_loss can execute on the GPU box above
+                                    gangealing_b200.compat (tests/test_reference_dropin_gpu.py: the "drops in
+                                    unchanged" claim of SURVEY.md 8(b)).  models/stylegan2/op and
+                                    models/spatial_transformers/antialiased_sampling.py are NOT compiled: those are
+                                    the kernel boundary the shim replaces.
 """
 import os
 import shutil
@@ -49,7 +57,37 @@ def build(verbose=False):
             shutil.copy(os.path.join(bdir, name + ".so"), target)
             shutil.rmtree(bdir, ignore_errors=True)
         built.append(target)
+    built.append(build_refpy())
     return built
+
+
+REFPY = os.path.join(OUT, "refpy")
+_REFPY_SKIP = (os.path.join("models", "stylegan2", "op"), os.path.join("models", "spatial_transformers", "antialiased_sampling.py"))
+_REFPY_UTILS = ("__init__.py", "distributed.py", "download.py", "annealing.py")
+
+
+def build_refpy():
+    """Byte-compile the reference's network code into oracle/_ref/refpy (sourceless .pyc tree)."""
+    import py_compile
+    todo = []
+    for base, _, files in os.walk(os.path.join(REF, "models")):
+        for f in files:
+            if f.endswith(".py"):
+                rel = os.path.relpath(os.path.join(base, f), REF)
+                if not any(rel.startswith(s) for s in _REFPY_SKIP):
+                    todo.append(rel)
+    todo += [os.path.join("utils", f) for f in _REFPY_UTILS if os.path.exists(os.path.join(REF, "utils", f))]
+    for rel in todo:
+        dst = os.path.join(REFPY, rel + "c")
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        # dfile: tracebacks name the reference file, not a path inside this repo
+        py_compile.compile(os.path.join(REF, rel), cfile=dst, dfile=os.path.join("<reference>", rel), doraise=True,
+                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    return REFPY
+
+
+def refpy_available():
+    return os.path.exists(os.path.join(REFPY, "models", "__init__.pyc"))
 
 
 def load_ref(name):

@@ -29,26 +29,66 @@ def test_oracle_matches_reference_fixture():
         assert_close(gb, g1, rtol=1e-6, what=name + " g1")
 
 
-def test_device_side_composite_is_the_same_formula_and_the_op_refuses_cpu_tensors():
-    from gangealing_b200.op.feature_distance import _composite, feature_distance
+def test_the_op_refuses_cpu_tensors_and_has_no_eager_route():
+    from gangealing_b200.op import feature_distance as mod
     g = torch.Generator().manual_seed(2)
     a, b = torch.rand(2, 12, 5, 5, generator=g), torch.rand(2, 12, 5, 5, generator=g)
-    w = torch.rand(12, generator=g)
-    assert_close(_composite(a, b, w, 1e-10), feature_distance_ref(a, b, w), rtol=1e-6)   # the unsupported-layout route
     with pytest.raises(RuntimeError):
-        feature_distance(a, b, w)                                                         # no CPU path in the product
+        mod.feature_distance(a, b, torch.rand(12, generator=g))                           # no CPU path in the product
+    assert not hasattr(mod, "_composite")                                                 # and no tensor-op fallback
+    assert mod._channels_ok(64) and mod._channels_ok(512) and mod._channels_ok(16) and not mod._channels_ok(12)
+
+
+def test_perceptual_module_is_key_compatible_with_the_reference_lpips():
+    """Reference LPIPS checkpoints (`scaling_layer.*`, `net.slice{k}.{torchvision index}.*`, `lin{k}.model.1.weight`) and
+    torchvision VGG16 `features` checkpoints (lpips_backbones.py:103-105) load into the mirror."""
+    from gangealing_b200.training.perceptual import PerceptualLoss, get_perceptual_loss
+    base = PerceptualLoss()
+    keys = set(base.state_dict().keys())
+    conv_idx = {1: (0, 2), 2: (5, 7), 3: (10, 12, 14), 4: (17, 19, 21), 5: (24, 26, 28)}
+    want = {"scaling_layer.shift", "scaling_layer.scale"}
+    for k, idxs in conv_idx.items():
+        for i in idxs:
+            want |= {"net.slice%d.%d.weight" % (k, i), "net.slice%d.%d.bias" % (k, i)}
+    assert keys == want
+    lp = PerceptualLoss(divisor=1.0, lpips=True)
+    assert {"lin%d.model.1.weight" % k for k in range(5)} <= set(lp.state_dict().keys())
+    # a torchvision-style features state dict loads strictly and lands in the right slices
+    g = torch.Generator().manual_seed(0)
+    feats = {}
+    for k, idxs in conv_idx.items():
+        for i in idxs:
+            w = dict(getattr(base.net, "slice%d" % k).named_children())[str(i)].weight
+            feats["%d.weight" % i] = torch.randn(w.shape, generator=g)
+            feats["%d.bias" % i] = torch.randn(w.shape[0], generator=g)
+    loaded = PerceptualLoss(pretrained_weights=feats)
+    assert torch.equal(loaded.state_dict()["net.slice3.12.weight"], feats["12.weight"])
+    with pytest.raises(RuntimeError):
+        PerceptualLoss(pretrained_weights=dict(feats, **{"30.weight": torch.zeros(1)}))    # strict, like the reference
+    assert get_perceptual_loss("cpu", kind="lpips").lpips
+
+
+@pytest.mark.skipif(not __import__("oracle.refimport", fromlist=["x"]).available(), reason="reference checkout not present")
+def test_reference_lpips_state_dict_loads_into_the_mirror():
+    from oracle import refimport
+    refimport.import_reference()
+    import models.losses.lpips as L
+    from gangealing_b200.training.perceptual import PerceptualLoss
+    for lpips in (False, True):
+        ref = L.LPIPS(net="vgg", lpips=lpips, pnet_rand=True, pretrained=False, verbose=False)
+        ours = PerceptualLoss(lpips=lpips)
+        missing, unexpected = ours.load_state_dict(ref.state_dict(), strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
 
 
 @pytest.mark.gpu
 def test_fused_kernels_match_reference_fixture():
-    from gangealing_b200.op.feature_distance import feature_distance, _supported
+    from gangealing_b200.op.feature_distance import feature_distance
     blob = load_golden("perceptual")
     for name in golden_cases(blob):
         f0, f1, w, out, gout, g0, g1 = _case(blob, name)
         a = f0.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
         b = f1.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
-        if a.shape[2] * a.shape[3] > 1 and a.shape[1] > 1:
-            assert _supported(a, b), name
         res = feature_distance(a, b, None if w is None else w.to(DEV))
         assert_close(res, out, rtol=1e-5, what=name + " out")
         ga, gb = torch.autograd.grad(res, [a, b], gout.to(DEV))
@@ -79,6 +119,10 @@ def test_fused_kernels_match_oracle(shape):
     # symmetry and identity: d(a, b) == d(b, a), d(a, a) == 0 -- size-independent properties
     assert_close(feature_distance(y, x), r, rtol=1e-6)
     assert float(feature_distance(x, x).abs().max()) < 1e-12   # a*ia - b*ib contracts to an fma: one rounding residual
+    # planar (NCHW) and half-precision maps are converted to the kernel's layout, never evaluated with tensor ops
+    assert_close(feature_distance(f0.to(DEV), f1.to(DEV)), ro, rtol=1e-5, what="NCHW input")
+    assert_close(feature_distance(x.detach().bfloat16(), y.detach().bfloat16()),
+                 feature_distance_ref(f0.bfloat16().float(), f1.bfloat16().float()), rtol=1e-5, what="bf16 input")
 
 
 def test_whole_perceptual_loss_matches_the_reference_lpips_fixture():

@@ -81,8 +81,119 @@ def nhwc_family(B, dev, k4, timeit, report, pool_count):
         del ys
 
 
+def reference_bar(B, dev, k4, timeit, pool_count, peak, json_path):
+    """The kernel bar (BASELINE.md section 3 / SURVEY.md 8d): the reference's own CUDA kernels recompiled for sm_100a
+    (oracle/_ref/*.so: upfirdn2d_kernel.cu:209-369, fused_bias_act_kernel.cu:52-99, splat_gpu_impl.cu:41-96) timed at the
+    hot-path shapes on this GPU, next to this repo's kernels on the same inputs.  tools/ is test infrastructure."""
+    from oracle import build_ref
+    from gangealing_b200.splat2d import splat2d
+    up_ref, fused_ref, splat_ref = build_ref.load_ref("upfirdn2d_ref"), build_ref.load_ref("fused_ref"), build_ref.load_splat_ref()
+    if up_ref is None or fused_ref is None:
+        raise SystemExit("oracle/_ref/*.so not built (python -m oracle.build_ref in the build container)")
+    CL = torch.channels_last
+    rows = []
+
+    def add(name, nbytes, ms_ref, ms_nchw, ms_nhwc):
+        row = {"op": name, "MB": nbytes / 1e6, "reference_ms": ms_ref, "ours_nchw_ms": ms_nchw, "ours_nhwc_ms": ms_nhwc,
+               "reference_GBs": nbytes / ms_ref / 1e6,
+               "ours_nchw_GBs": nbytes / ms_nchw / 1e6 if ms_nchw else None,
+               "ours_nhwc_GBs": nbytes / ms_nhwc / 1e6 if ms_nhwc else None}
+        best = min(m for m in (ms_nchw, ms_nhwc) if m)
+        row["speedup_best"] = ms_ref / best
+        row["ours_best_frac_of_peak"] = nbytes / best / 1e6 / peak
+        rows.append(row)
+        print("%-52s ref %8.3f ms | ours nchw %8s  nhwc %8s ms | x%5.2f  (%4.1f%% of peak)" % (
+            name, ms_ref, "%.3f" % ms_nchw if ms_nchw else "-", "%.3f" % ms_nhwc if ms_nhwc else "-", row["speedup_best"],
+            100 * row["ours_best_frac_of_peak"]))
+
+    def ref_up(x, up=1, down=1, pad=(1, 1)):
+        n, c, h, w = x.shape
+        return up_ref.upfirdn2d(x.reshape(-1, h, w, 1), k4, up, up, down, down, pad[0], pad[1], pad[0], pad[1])
+
+    for C, H in [(128, 256), (256, 128), (512, 64), (512, 32), (512, 16), (512, 8)]:
+        hin = H + 1
+        nbytes = 4 * B * C * (hin * hin + H * H)
+        P = pool_count(nbytes)
+        xs = [torch.randn(B, C, hin, hin, device=dev) for _ in range(P)]
+        xl = [x.contiguous(memory_format=CL) for x in xs]
+        noise = torch.randn(B, 1, H, H, device=dev)
+        nw = torch.tensor([0.1], device=dev)
+        bias = torch.randn(C, device=dev)
+        empty = xs[0].new_empty(0)
+        add("upfirdn2d blur C=%d %d->%d" % (C, hin, H), nbytes,
+            timeit(lambda i: ref_up(xs[i]), P), timeit(lambda i: op.upfirdn2d(xs[i], k4, pad=(1, 1)), P),
+            timeit(lambda i: op.upfirdn2d(xl[i], k4, pad=(1, 1)), P))
+
+        def ref_tail(i):    # Blur -> NoiseInjection -> FusedLeakyReLU, networks.py:266,291-298,346-348
+            t = ref_up(xs[i]).view(B, C, H, H)
+            t = t + nw * noise
+            return fused_ref.fused_bias_act(t, bias, empty, 3, 0, 0.2, 2 ** 0.5)
+        add("StyledConv-up tail (blur+noise+bias+lrelu) C=%d %d" % (C, H), nbytes + 4 * B * H * H,
+            timeit(ref_tail, P), timeit(lambda i: op.blur_noise_bias_act(xs[i], k4, (1, 1), noise, nw, bias), P),
+            timeit(lambda i: op.blur_noise_bias_act(xl[i], k4, (1, 1), noise, nw, bias), P))
+        del xs, xl
+        ys = [torch.randn(B, C, H, H, device=dev) for _ in range(P)]
+        yl = [y.contiguous(memory_format=CL) for y in ys]
+        nb2 = 4 * B * C * H * H * 2
+        add("fused_bias_act fwd C=%d %d^2" % (C, H), nb2,
+            timeit(lambda i: fused_ref.fused_bias_act(ys[i], bias, empty, 3, 0, 0.2, 2 ** 0.5), P),
+            timeit(lambda i: op.fused_leaky_relu(ys[i], bias), P), timeit(lambda i: op.fused_leaky_relu(yl[i], bias), P))
+
+        def ref_plain_tail(i):
+            return fused_ref.fused_bias_act(ys[i] + nw * noise, bias, empty, 3, 0, 0.2, 2 ** 0.5)
+        add("StyledConv tail (noise+bias+lrelu) C=%d %d^2" % (C, H), nb2 + 4 * B * H * H,
+            timeit(ref_plain_tail, P), timeit(lambda i: op.noise_bias_act(ys[i], noise, nw, bias), P),
+            timeit(lambda i: op.noise_bias_act(yl[i], noise, nw, bias), P))
+
+        def ref_bwd(i):     # fused_act.py:29-38: act-grad kernel, then a second pass for the bias gradient
+            gx = fused_ref.fused_bias_act(ys[i], empty, ys[(i + 1) % P], 3, 1, 0.2, 2 ** 0.5)
+            return gx, gx.sum([0, 2, 3])
+        add("fused_bias_act bwd (+bias grad) C=%d %d^2" % (C, H), 4 * B * C * H * H * 3,
+            timeit(ref_bwd, P), timeit(lambda i: bias_act_backward_raw(ys[i], ys[(i + 1) % P], 0.2, 2 ** 0.5, True), P),
+            timeit(lambda i: bias_act_backward_raw(yl[i], yl[(i + 1) % P], 0.2, 2 ** 0.5, True), P))
+        del ys, yl
+    for H in (128, 64):
+        x = torch.randn(B, 3, H, H, device=dev)
+        add("upfirdn2d rgb up2 %d->%d" % (H, 2 * H), 4 * B * 3 * 5 * H * H,
+            timeit(lambda i: ref_up(x, 2, 1, (2, 1)), 1), timeit(lambda i: op.upfirdn2d(x, k4, up=2, pad=(2, 1)), 1), None)
+    for C, H, pad in [(64, 128, (2, 2)), (64, 128, (1, 1)), (128, 64, (2, 2)), (512, 32, (2, 2))]:
+        x = [torch.randn(B, C, H, H, device=dev) for _ in range(4)]
+        xl = [t.contiguous(memory_format=CL) for t in x]
+        ho = H + 2 * pad[0] - 3
+        add("upfirdn2d stn blur C=%d %d pad%s" % (C, H, pad), 4 * B * C * (H * H + ho * ho),
+            timeit(lambda i: ref_up(x[i], 1, 1, pad), 4), timeit(lambda i: op.upfirdn2d(x[i], k4, pad=pad), 4),
+            timeit(lambda i: op.upfirdn2d(xl[i], k4, pad=pad), 4))
+    # splat2d, BASELINE config 4: a dense disc of P points into 512^2, sigma 0.3 / 1.3 (propagate_to_images.py:44-78)
+    if splat_ref is not None:
+        for R, sigma in [(256, 0.3), (256, 1.3), (1024, 0.3), (1024, 1.3)]:
+            ys_, xs_ = torch.meshgrid(torch.arange(float(R)), torch.arange(float(R)), indexing="ij")
+            disc = ((ys_ - R / 2) ** 2 + (xs_ - R / 2) ** 2) < (0.35 * R) ** 2
+            pts = (torch.stack([xs_[disc], ys_[disc]], 1) * (511.0 / (R - 1)) + 0.25)[None].to(dev).contiguous()
+            Pn = pts.shape[1]
+            vals = torch.randn(1, Pn, 3, device=dev)
+            sig = torch.tensor([sigma], device=dev)
+            blank = torch.zeros(1, 3, 512, 512, device=dev)
+            alpha = torch.zeros(1, 512, 512, device=dev)
+
+            def ref_splat(i):   # splat_gpu.c:20-41 host sequence around the reference kernel
+                alpha.zero_()
+                acc = blank.clone()
+                splat_ref.SplatForwardGpu(torch.cuda.current_stream().cuda_stream, pts.data_ptr(), vals.data_ptr(), sig.data_ptr(),
+                                          alpha.data_ptr(), acc.data_ptr(), Pn, 3, 512, 512, Pn)
+                return acc / (alpha.view(1, 1, 512, 512) + 1e-8)
+            nbytes = 4 * (Pn * 5 + 4 * 512 * 512 + 2 * 3 * 512 * 512)
+            add("splat2d 512^2 P=%d sigma=%.1f" % (Pn, sigma), nbytes, timeit(ref_splat, 1),
+                timeit(lambda i: splat2d(blank, pts, vals, sig, False), 1), None)
+    if json_path:
+        os.makedirs(os.path.dirname(os.path.abspath(json_path)), exist_ok=True)
+        json.dump({"batch": B, "dtype": "float32", "peak_gbs": peak,
+                   "what": "reference CUDA kernels (recompiled sm_100a) vs this repo, same inputs, CUDA events, >L2 input pools",
+                   "rows": rows}, open(json_path, "w"), indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", action="store_true", help="time the reference's own CUDA kernels (oracle/_ref) next to ours")
     ap.add_argument("--batch", type=int, default=5)
     ap.add_argument("--json", default=None)
     ap.add_argument("--dtype", default="float32")
@@ -105,6 +216,9 @@ def main():
     def pool_count(nbytes):
         return max(2, min(8, int(400e6 // max(nbytes, 1)) + 1))
 
+    if args.ref:
+        reference_bar(B, dev, k4, timeit, pool_count, peak, args.json)
+        return
     if args.layout == "nhwc":
         nhwc_family(B, dev, k4, timeit, report, pool_count)
         if args.json:
