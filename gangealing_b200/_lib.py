@@ -39,11 +39,15 @@ SIGNATURES = {
     "gg_modconv_wsq": (_I, [_P, _P, _I, _I, _I, _P]),
     "gg_modconv_demod": (_I, [_P, _P, _P, _F, _F, _I, _I, _I, _P]),
     "gg_modconv_modulate": (_I, [_P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P]),
-    "gg_noise_bias_act_nhwc": (_I, [_P] * 6 + [_F, _F, _L, _I, _L, _P]),
+    "gg_noise_bias_act_nhwc": (_I, [_P] * 6 + [_I, _F, _F, _L, _I, _L, _P]),
     "gg_nhwc_rowwise_workspace": (_L, [_L, _I, _L]),
-    "gg_channel_scale_nhwc": (_I, [_P] * 6 + [_L, _I, _L, _P]),
-    "gg_bias_act_backward_nhwc": (_I, [_P] * 5 + [_F, _F, _L, _I, _L, _P]),
-    "gg_blur_nhwc": (_I, [_P] * 7 + [_L] + [_I] * 12 + [_F, _F, _P]),
+    "gg_channel_scale_nhwc": (_I, [_P] * 6 + [_I, _L, _I, _L, _P]),
+    "gg_bias_act_backward_nhwc": (_I, [_P] * 5 + [_I, _F, _F, _L, _I, _L, _P]),
+    "gg_blur_nhwc_workspace": (_L, [_I, _L] + [_I] * 9),
+    "gg_blur_nhwc": (_I, [_P] * 12 + [_I, _L] + [_I] * 12 + [_F, _F, _P]),
+    "gg_styled_tail_nhwc": (_I, [_P] * 12 + [_I, _I, _F, _F, _L, _I, _L, _P]),
+    "gg_styled_tail_backward_workspace": (_L, [_I, _L, _I, _L]),
+    "gg_styled_tail_backward_nhwc": (_I, [_P] * 12 + [_I, _F, _F, _L, _I, _L, _P]),
     "gg_tent_downsample_forward": (_I, [_P] * 4 + [_L, _I, _I, _I, _I, _P]),
     "gg_tent_downsample_backward": (_I, [_P] * 4 + [_L, _I, _I, _I, _I, _P]),
     "gg_feature_distance_workspace": (_L, [_L, _I, _L]),
@@ -119,9 +123,15 @@ def ptr(t):
 
 
 def is_nhwc(t):
-    """True for a 4-D fp32 tensor stored channels-last (and not also plain-contiguous)."""
-    return (t.dim() == 4 and t.dtype == torch.float32 and t.shape[1] > 1 and t.shape[2] * t.shape[3] > 1
+    """True for a 4-D fp32 / bf16 tensor stored channels-last (and not also plain-contiguous).  The channels-last kernel
+    family moves 16 bytes of channels at a time: callers additionally check C % nhwc_vec(t) (or the blur's multiple)."""
+    return (t.dim() == 4 and t.dtype in (torch.float32, torch.bfloat16) and t.shape[1] > 1 and t.shape[2] * t.shape[3] > 1
             and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous())
+
+
+def nhwc_vec(t):
+    """Channels per 16-byte access of the channels-last kernels: 4 (fp32) or 8 (bf16)."""
+    return 8 if t.dtype == torch.bfloat16 else 4
 
 
 def tensor_cache(t):

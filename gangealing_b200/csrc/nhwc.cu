@@ -7,6 +7,9 @@
 // EVERYTHING is 16-byte aligned: the blur can use a real 4-D TMA tensor map (cp.async.bulk.tensor, SASS UTMALDG)
 // whose out-of-bounds zero fill implements the padding of upfirdn2d for free.
 //
+// Every kernel is templated on the STORAGE type T (fp32, or bf16 for BASELINE config 3: bf16 activations, fp32
+// arithmetic); an activation is always moved 16 bytes at a time (V = 4 fp32 / 8 bf16 channels, ChanVec<T>).
+//
 // Same math / reference citations as the NCHW kernels (bias_act.cu, upfirdn2d.cu):
 //   gg_noise_bias_act_nhwc       lrelu(rs[n,c]*x + nw*noise[n,p] + b[c])*gain                networks.py:291-298,346-348
 //   gg_bias_act_backward_nhwc    gx = (out>0 ? g : a*g)*gain ; grad_bias[c] = sum gx          op/fused_act.py:20-38
@@ -15,6 +18,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "nhwc_reduce.cuh"
 
 namespace gg {
 namespace {
@@ -22,145 +26,124 @@ namespace {
 constexpr int kT = 256;
 
 // ------------------------------------------------------------------------------------------------ elementwise
+template <typename T>
 __global__ void __launch_bounds__(kT)
-noise_bias_act_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ noise,
+noise_bias_act_nhwc_kernel(T* __restrict__ out, const T* __restrict__ x, const float* __restrict__ noise,
                            const float* __restrict__ noise_weight, const float* __restrict__ bias,
-                           const float* __restrict__ row_scale, float alpha, float gain, int64_t n_vec, int c4,
+                           const float* __restrict__ row_scale, float alpha, float gain, int64_t n_vec, int cv,
                            int64_t hw) {
+  constexpr int V = ChanVec<T>::V;
   const float nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
   const int64_t base = (static_cast<int64_t>(blockIdx.x) * 4) * kT + threadIdx.x;
-  Vec16<float> xv[4];
+  uint4 xv[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int64_t v = base + static_cast<int64_t>(u) * kT;
-    if (v < n_vec) xv[u] = ld_vec_stream(x + v * 4);
+    if (v < n_vec) xv[u] = ldg_stream16(x + v * V);
   }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int64_t v = base + static_cast<int64_t>(u) * kT;
     if (v < n_vec) {
-      const int64_t pix = v / c4;                      // n*hw + p
-      const int cq = static_cast<int>(v - pix * c4);
+      const int64_t pix = v / cv;                      // n*hw + p
+      const int cq = static_cast<int>(v - pix * cv);
       const int64_t n = pix / hw;
-      const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 r = row_scale ? __ldg(reinterpret_cast<const float4*>(row_scale + n * c4 * 4) + cq)
-                                 : make_float4(1.f, 1.f, 1.f, 1.f);
       const float nz = noise ? nw * __ldg(noise + pix) : 0.f;
-      const float bb[4] = {b.x, b.y, b.z, b.w}, rr[4] = {r.x, r.y, r.z, r.w};
-      Vec16<float> o;
+      float xf[V], o[V];
+      ChanVec<T>::unpack(xv[u], xf);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float t = fmaf(xv[u].v[k], rr[k], bb[k]) + nz;
-        o.v[k] = (t > 0.f ? t : t * alpha) * gain;
+      for (int q = 0; q < V / 4; ++q) {
+        const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq * (V / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 r = row_scale ? __ldg(reinterpret_cast<const float4*>(row_scale + n * cv * V) + cq * (V / 4) + q)
+                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float bb[4] = {b.x, b.y, b.z, b.w}, rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float t = fmaf(xf[4 * q + k], rr[k], bb[k]) + nz;
+          o[4 * q + k] = (t > 0.f ? t : t * alpha) * gain;
+        }
       }
-      st_vec_stream(out + v * 4, o);
+      stg_stream16(out + v * V, ChanVec<T>::pack(o));
     }
   }
 }
 
-// One CTA = `rows` consecutive pixels of one sample x all channels.  Thread = (channel quad, pixel lane); per-channel
+// One CTA = `chunk` consecutive pixels of one sample x all channels.  Thread = (channel vector, pixel lane); per-channel
 // sums are reduced across the CTA's pixel lanes in shared memory and written as one partial row per CTA.
 // MODE 0: channel_scale (out = x*s, dot = sum x*y)   MODE 1: bias_act backward (out = act'(ref)*x*gain, dot = sum out)
-template <int MODE>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kT)
-rowwise_nhwc_kernel(float* __restrict__ out, float* __restrict__ partial, const float* __restrict__ x,
-                    const float* __restrict__ y, const float* __restrict__ s, float alpha, float gain, int c4,
+rowwise_nhwc_kernel(T* __restrict__ out, float* __restrict__ partial, const T* __restrict__ x,
+                    const T* __restrict__ y, const float* __restrict__ s, float alpha, float gain, int cv,
                     int64_t hw, int chunk, int chunks_per_sample) {
+  constexpr int V = ChanVec<T>::V;
   extern __shared__ float red[];                       // [pixel lanes][C] partial sums
   const int64_t n = blockIdx.x / chunks_per_sample;
   const int ck = blockIdx.x - n * chunks_per_sample;
   const int64_t p0 = static_cast<int64_t>(ck) * chunk, p1 = min(p0 + chunk, hw);
-  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;       // pixel lanes when C/4 <= 256
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // a thread owns channel quads cq = tid % c4 (+ k*kT when c4 > kT is not supported: C <= 1024)
-  const int cq = threadIdx.x % c4;
-  const int pl = threadIdx.x / c4;
+  const int lanes_p = kT / cv > 0 ? kT / cv : 1;       // pixel lanes when C/V <= 256
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  const int cq = threadIdx.x % cv;
+  const int pl = threadIdx.x / cv;
   if (pl < lanes_p) {
-    float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (MODE == 0) sv = __ldg(reinterpret_cast<const float4*>(s + n * c4 * 4) + cq);
-    auto body = [&](const float4 xv, const float4 yv, int64_t off) {
-      float4 o;
-      if (MODE == 0) {
-        o = make_float4(xv.x * sv.x, xv.y * sv.y, xv.z * sv.z, xv.w * sv.w);
-        if (y) {
-          acc.x = fmaf(xv.x, yv.x, acc.x); acc.y = fmaf(xv.y, yv.y, acc.y);
-          acc.z = fmaf(xv.z, yv.z, acc.z); acc.w = fmaf(xv.w, yv.w, acc.w);
-        }
-      } else {                                 // y = saved forward output
-        o.x = (yv.x > 0.f ? xv.x : xv.x * alpha) * gain; o.y = (yv.y > 0.f ? xv.y : xv.y * alpha) * gain;
-        o.z = (yv.z > 0.f ? xv.z : xv.z * alpha) * gain; o.w = (yv.w > 0.f ? xv.w : xv.w * alpha) * gain;
-        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-      }
-      *reinterpret_cast<float4*>(out + off) = o;
-    };
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sv[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) sv[k] = (MODE == 0) ? __ldg(s + n * cv * V + cq * V + k) : 1.f;
     const bool has_y = (MODE == 1) || y != nullptr;
+    auto body = [&](const uint4 xr, const uint4 yr, int64_t off) {
+      float xf[V], yf[V], o[V];
+      ChanVec<T>::unpack(xr, xf);
+      ChanVec<T>::unpack(yr, yf);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if (MODE == 0) {
+          o[k] = xf[k] * sv[k];
+          if (has_y) acc[k] = fmaf(xf[k], yf[k], acc[k]);
+        } else {                                 // y = saved forward output
+          o[k] = (yf[k] > 0.f ? xf[k] : xf[k] * alpha) * gain;
+          acc[k] += o[k];
+        }
+      }
+      *reinterpret_cast<uint4*>(out + off) = ChanVec<T>::pack(o);
+    };
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     int64_t p = p0 + pl;
     // 4 pixels per trip: all loads issued before the first dependent store (memory-level parallelism)
     for (; p + 3 * lanes_p < p1; p += 4 * lanes_p) {
-      float4 xv[4], yv[4];
+      uint4 xv[4], yv[4];
       int64_t off[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        off[u] = ((n * hw + p + u * lanes_p) * c4 + cq) * 4;
-        xv[u] = __ldcs(reinterpret_cast<const float4*>(x + off[u]));
+        off[u] = ((n * hw + p + u * lanes_p) * cv + cq) * V;
+        xv[u] = ldg_stream16(x + off[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) yv[u] = has_y ? __ldcs(reinterpret_cast<const float4*>(y + off[u])) : zero;
+      for (int u = 0; u < 4; ++u) yv[u] = has_y ? ldg_stream16(y + off[u]) : zero;
 #pragma unroll
       for (int u = 0; u < 4; ++u) body(xv[u], yv[u], off[u]);
     }
     for (; p < p1; p += lanes_p) {
-      const int64_t off = ((n * hw + p) * c4 + cq) * 4;
-      const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + off));
-      const float4 yv = has_y ? __ldcs(reinterpret_cast<const float4*>(y + off)) : zero;
+      const int64_t off = ((n * hw + p) * cv + cq) * V;
+      const uint4 xv = ldg_stream16(x + off);
+      const uint4 yv = has_y ? ldg_stream16(y + off) : zero;
       body(xv, yv, off);
     }
   }
   if (partial) {
-    float4* r4 = reinterpret_cast<float4*>(red);
-    if (pl < lanes_p) r4[pl * c4 + cq] = acc;
-    __syncthreads();
-    if (threadIdx.x < c4) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int l = 0; l < lanes_p; ++l) {
-        const float4 v = r4[l * c4 + threadIdx.x];
-        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-      }
-      reinterpret_cast<float4*>(partial + static_cast<int64_t>(blockIdx.x) * c4 * 4)[threadIdx.x] = t;
-    }
-  }
-}
-
-// dst[r][c] = sum_k partial[(r*K + k)][c]    (r = sample for channel_scale; a single row for grad_bias)
-// CTA = 32 channels x 32 k-lanes: each lane sums every 32nd partial row (4 independent loads per trip), then the
-// 32 lane sums are combined through shared memory in a fixed order (deterministic).
-__global__ void __launch_bounds__(1024)
-nhwc_finish_kernel(float* __restrict__ dst, const float* __restrict__ partial, int64_t rows, int K, int C) {
-  __shared__ float red[32][33];
-  const int cblocks = (C + 31) / 32;
-  const int64_t r = blockIdx.x / cblocks;
-  const int c = (blockIdx.x - r * cblocks) * 32 + threadIdx.x;
-  const int ky = threadIdx.y;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  if (c < C) {
-    const float* base = partial + r * K * C + c;
-    int k = ky;
-    for (; k + 96 < K; k += 128) {
-      a0 += base[static_cast<int64_t>(k) * C];
-      a1 += base[static_cast<int64_t>(k + 32) * C];
-      a2 += base[static_cast<int64_t>(k + 64) * C];
-      a3 += base[static_cast<int64_t>(k + 96) * C];
-    }
-    for (; k < K; k += 32) a0 += base[static_cast<int64_t>(k) * C];
-  }
-  red[ky][threadIdx.x] = (a0 + a1) + (a2 + a3);
-  __syncthreads();
-  if (ky == 0 && c < C) {
-    float t = 0.f;
+    const int C = cv * V;
+    if (pl < lanes_p) {
 #pragma unroll
-    for (int q = 0; q < 32; ++q) t += red[q][threadIdx.x];
-    dst[r * C + c] = t;
+      for (int q = 0; q < V / 4; ++q)
+        reinterpret_cast<float4*>(red + pl * C + cq * V)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kT) {
+      float t = 0.f;
+      for (int l = 0; l < lanes_p; ++l) t += red[l * C + c];
+      partial[static_cast<int64_t>(blockIdx.x) * C + c] = t;
+    }
   }
 }
 
@@ -299,12 +282,19 @@ to_rgb_nhwc_bwd_kernel(float* __restrict__ gx, float* __restrict__ partial, cons
 }
 
 // ------------------------------------------------------------------------------------------------ blur (TMA tiled)
-constexpr int kCB = 32;     // channels per CTA (128 B per pixel in the tile)
-constexpr int kBX = 64;     // output columns per CTA; a thread owns 2 adjacent columns x 4 channels
+// Tile geometry per storage type: a thread always owns 16 bytes of channels (V = 4 fp32 / 8 bf16) so that a pixel of the
+// tile is 128 bytes (8 threads, conflict-free LDS.128); it owns COLS adjacent output columns (2 for fp32, 1 for bf16:
+// the register window is 4 rows x COLS x V floats either way).
+template <typename T> struct BlurGeom {
+  static constexpr int V = ChanVec<T>::V;
+  static constexpr int CB = 8 * V;                 // channels per CTA (128 B per pixel in the tile)
+  static constexpr int COLS = (V == 4) ? 2 : 1;    // output columns per thread
+  static constexpr int BX = 32 * COLS;             // output columns per CTA
+  static constexpr int TW = BX + 3;                // tile width (3 halo columns)
+  static constexpr int STAGE_ELEMS = 4 * TW * CB;  // kRY = 4 rows per stage
+};
 constexpr int kRY = 4;      // input rows per pipeline stage
 constexpr int kNS = 3;      // stages
-constexpr int kTileW = kBX + 3;
-constexpr int kStageFloats = kRY * kTileW * kCB;
 
 struct BlurNhwcParams {
   int n, c, in_h, in_w, out_h, out_w;
@@ -322,31 +312,43 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
-// CTA = (sample n, 64-column block, 32-channel chunk, row segment).  Input rows stream through a 3-stage ring of
-// {32 ch x 67 px x 4 rows} TMA boxes (zero-filled outside the image = upfirdn2d's padding); each thread slides a
-// 4-row window of horizontal results for its 2 columns x 4 channels down the whole segment, so a row is read from
-// shared memory once and from HBM once (+3 halo rows per segment, +3/64 halo columns).
-template <bool FUSED, bool SEP>
+// CTA = (sample n, BX-column block, CB-channel chunk, row segment).  Input rows stream through a 3-stage ring of
+// {CB ch x TW px x 4 rows} TMA boxes (zero-filled outside the image = upfirdn2d's padding); each thread slides a
+// 4-row window of horizontal results for its COLS columns x V channels down the whole segment, so a row is read from
+// shared memory once and from HBM once (+3 halo rows per segment, +3/BX halo columns).
+//   MODE 0  plain blur                                                  out = B(in)
+//   MODE 1  fused StyledConv tail: o = lrelu(rs*B(in) + nw*noise + b)*gain; writes `out` = o and/or `out2` = o*scale2[n,c]
+//           (the NEXT modulated convolution's input: its style modulation rides in this epilogue, networks.py:236,243)
+//   MODE 2  adjoint epilogue (backward of MODE 1's blur): t = B(in); `out` = t*rs[n,c]; partial[cta][c] = sum t*mul[n,y,x,c]
+//           (the gradient of the demodulation coefficients, <B^T g, raw>, reduced inside the pass that produces B^T g)
+template <typename T, int MODE, bool SEP>
 __global__ void __launch_bounds__(kT, 2)
-blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tmap, const float* __restrict__ filt,
-                 int kh, int kw, const float* __restrict__ noise, const float* __restrict__ noise_weight,
-                 const float* __restrict__ bias, const float* __restrict__ row_scale, BlurNhwcParams p) {
-  extern __shared__ __align__(128) float tiles[];
+blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constant__ CUtensorMap tmap,
+                 const float* __restrict__ filt, int kh, int kw, const float* __restrict__ noise,
+                 const float* __restrict__ noise_weight, const float* __restrict__ bias,
+                 const float* __restrict__ row_scale, const float* __restrict__ scale2, const T* __restrict__ mul,
+                 float* __restrict__ partial, BlurNhwcParams p) {
+  using G = BlurGeom<T>;
+  constexpr int V = G::V, CB = G::CB, COLS = G::COLS, BX = G::BX, TW = G::TW;
+  constexpr bool FUSED = MODE == 1;
+  extern __shared__ __align__(128) unsigned char tiles_raw[];
+  T* tiles = reinterpret_cast<T*>(tiles_raw);
   __shared__ uint64_t full_bar[kNS];
   const int tid = threadIdx.x;
-  const int cq = tid & 7;                 // channel quad within the 32-channel chunk
-  const int xg = tid >> 3;                // 0..31 -> columns 2*xg, 2*xg+1 of the block
-  const int chunks = p.c / kCB;
+  const int cq = tid & 7;                 // channel vector within the CB-channel chunk
+  const int xg = tid >> 3;                // 0..31 -> columns COLS*xg .. of the block
+  const int chunks = p.c / CB;
   const int bx = blockIdx.x / chunks, cc = blockIdx.x - bx * chunks;
   const int n = blockIdx.z;
   const int oy0 = blockIdx.y * p.seg_rows;
   const int rows_out = min(p.seg_rows, p.out_h - oy0);
-  const int x_out0 = bx * kBX;            // first output column of the block
-  const int c0 = cc * kCB;
+  const int x_out0 = bx * BX;             // first output column of the block
+  const int c0 = cc * CB;
   // input row/col of tap (0,0) for output (oy0, x_out0)
   const int iy0 = oy0 - p.pad_y0, ix0 = x_out0 - p.pad_x0;
   const int rows_in = rows_out + 3;
   const int n_stage_iters = (rows_in + kRY - 1) / kRY;
+  constexpr uint32_t kStageBytes = G::STAGE_ELEMS * sizeof(T);
 
   if (tid == 0) {
 #pragma unroll
@@ -358,8 +360,8 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
 #pragma unroll
     for (int s = 0; s < kNS - 1; ++s)
       if (s < n_stage_iters) {
-        mbar_expect_tx(&full_bar[s], kStageFloats * 4);
-        tma_load_4d(tiles + s * kStageFloats, &tmap, c0, ix0, iy0 + s * kRY, n, &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        tma_load_4d(tiles + s * G::STAGE_ELEMS, &tmap, c0, ix0, iy0 + s * kRY, n, &full_bar[s]);
       }
   }
 
@@ -402,12 +404,27 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
     }
   }
 
-  // per-thread channel constants (a thread keeps its 4 channels for the whole segment)
-  float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = make_float4(1.f, 1.f, 1.f, 1.f);
+  // per-thread channel constants (a thread keeps its V channels for the whole segment)
+  float bq[V], rq[V], sq[V], dacc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { bq[k] = 0.f; rq[k] = 1.f; sq[k] = 1.f; dacc[k] = 0.f; }
   float nw = 0.f;
+  const int64_t nc0 = static_cast<int64_t>(n) * p.c + c0 + cq * V;
+  if (MODE != 0) {
+    if (row_scale) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) rq[k] = __ldg(row_scale + nc0 + k);
+    }
+  }
   if (FUSED) {
-    if (bias) bq = __ldg(reinterpret_cast<const float4*>(bias + c0) + cq);
-    if (row_scale) rq = __ldg(reinterpret_cast<const float4*>(row_scale + static_cast<int64_t>(n) * p.c + c0) + cq);
+    if (bias) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) bq[k] = __ldg(bias + c0 + cq * V + k);
+    }
+    if (scale2) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) sq[k] = __ldg(scale2 + nc0 + k);
+    }
     nw = noise ? (noise_weight ? __ldg(noise_weight) : 1.f) : 0.f;
   }
   // lrelu(t)*gain == max(T, T*slope) with T = gain*t when gain > 0 and 0 <= slope <= 1: the gain is folded into the
@@ -415,36 +432,39 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
   const bool fast = FUSED && p.gain > 0.f && ((p.act == 3 && p.alpha >= 0.f && p.alpha <= 1.f) || p.act == 1);
   const float neg = (p.act == 3) ? p.alpha : 1.f;
   if (fast) {
-    rq.x *= p.gain; rq.y *= p.gain; rq.z *= p.gain; rq.w *= p.gain;
-    bq.x *= p.gain; bq.y *= p.gain; bq.z *= p.gain; bq.w *= p.gain;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { rq[k] *= p.gain; bq[k] *= p.gain; }
     nw *= p.gain;
   }
-  float4 kur[4];                           // vertical taps x row scale (separable fused path)
+  const int xo = x_out0 + COLS * xg;      // first of this thread's output columns
+  bool okc[COLS];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) kur[a] = make_float4(ku[a] * rq.x, ku[a] * rq.y, ku[a] * rq.z, ku[a] * rq.w);
-  const int xo = x_out0 + 2 * xg;         // first of this thread's two output columns
-  const bool ok0 = xo < p.out_w, ok1 = xo + 1 < p.out_w;
+  for (int j = 0; j < COLS; ++j) okc[j] = xo + j < p.out_w;
   // noise of the rows a stage completes is fetched one stage ahead (its latency hides behind the previous stage)
-  float nzn[kRY][2];
+  float nzn[kRY][COLS];
 #pragma unroll
-  for (int rr = 0; rr < kRY; ++rr) nzn[rr][0] = nzn[rr][1] = 0.f;
+  for (int rr = 0; rr < kRY; ++rr)
+#pragma unroll
+    for (int j = 0; j < COLS; ++j) nzn[rr][j] = 0.f;
   auto fetch_noise = [&](int it_) {
 #pragma unroll
     for (int rr = 0; rr < kRY; ++rr) {
       const int ro = it_ * kRY + rr - 3;
-      nzn[rr][0] = nzn[rr][1] = 0.f;
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) nzn[rr][j] = 0.f;
       if (ro >= 0 && ro < rows_out) {
         const float* np_ = noise + (static_cast<int64_t>(n) * p.out_h + oy0 + ro) * p.out_w + xo;
-        if (ok0) nzn[rr][0] = __ldg(np_);
-        if (ok1) nzn[rr][1] = __ldg(np_ + 1);
+#pragma unroll
+        for (int j = 0; j < COLS; ++j)
+          if (okc[j]) nzn[rr][j] = __ldg(np_ + j);
       }
     }
   };
   if (FUSED && noise) fetch_noise(0);
 
-  // window: sep -> horizontal results hw[4 rows][2 cols] (float4 over channels); else raw inputs rw[4 rows][5 cols]
-  float4 hw[SEP ? 4 : 1][2];
-  float4 rw[SEP ? 1 : 4][5];
+  // window: sep -> horizontal results hwin[4 rows][COLS][V]; else raw inputs rwin[4 rows][COLS+3][V]
+  float hwin[SEP ? 4 : 1][COLS][V];
+  float rwin[SEP ? 1 : 4][COLS + 3][V];
   int r_in = 0;                            // input rows consumed so far (relative to iy0)
   for (int it = 0; it < n_stage_iters; ++it) {
     const int stage = it % kNS;
@@ -453,92 +473,110 @@ blur_nhwc_kernel(float* __restrict__ out, const __grid_constant__ CUtensorMap tm
       if (nxt < n_stage_iters) {
         const int ns = nxt % kNS;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full_bar[ns], kStageFloats * 4);
-        tma_load_4d(tiles + ns * kStageFloats, &tmap, c0, ix0, iy0 + nxt * kRY, n, &full_bar[ns]);
+        mbar_expect_tx(&full_bar[ns], kStageBytes);
+        tma_load_4d(tiles + ns * G::STAGE_ELEMS, &tmap, c0, ix0, iy0 + nxt * kRY, n, &full_bar[ns]);
       }
     }
-    float nzc[kRY][2];
+    float nzc[kRY][COLS];
 #pragma unroll
-    for (int rr = 0; rr < kRY; ++rr) { nzc[rr][0] = nzn[rr][0]; nzc[rr][1] = nzn[rr][1]; }
+    for (int rr = 0; rr < kRY; ++rr)
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) nzc[rr][j] = nzn[rr][j];
     if (FUSED && noise && it + 1 < n_stage_iters) fetch_noise(it + 1);
     mbar_wait(&full_bar[stage], static_cast<uint32_t>((it / kNS) & 1));
-    const float* st = tiles + stage * kStageFloats;
+    const T* st = tiles + stage * G::STAGE_ELEMS;
 #pragma unroll
     for (int rr = 0; rr < kRY; ++rr, ++r_in) {
-      // 5 input pixels (columns 2xg .. 2xg+4 of the tile) x 4 channels of this thread
-      const float4* rowp = reinterpret_cast<const float4*>(st + (rr * kTileW + 2 * xg) * kCB) + cq;
-      float4 q[5];
+      // COLS+3 input pixels (columns COLS*xg .. of the tile) x V channels of this thread
+      const uint4* rowp = reinterpret_cast<const uint4*>(st + (rr * TW + COLS * xg) * CB) + cq;
+      float q[COLS + 3][V];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) q[i] = rowp[i * (kCB / 4)];
+      for (int i = 0; i < COLS + 3; ++i) ChanVec<T>::unpack(rowp[i * 8], q[i]);     // pixel pitch = 8 x 16 B
       if constexpr (SEP) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float4 h;
-          h.x = fmaf(kv[3], q[j + 3].x, fmaf(kv[2], q[j + 2].x, fmaf(kv[1], q[j + 1].x, kv[0] * q[j].x)));
-          h.y = fmaf(kv[3], q[j + 3].y, fmaf(kv[2], q[j + 2].y, fmaf(kv[1], q[j + 1].y, kv[0] * q[j].y)));
-          h.z = fmaf(kv[3], q[j + 3].z, fmaf(kv[2], q[j + 2].z, fmaf(kv[1], q[j + 1].z, kv[0] * q[j].z)));
-          h.w = fmaf(kv[3], q[j + 3].w, fmaf(kv[2], q[j + 2].w, fmaf(kv[1], q[j + 1].w, kv[0] * q[j].w)));
-          hw[rr][j] = h;                   // kRY == 4: slot rr == r_in & 3
-        }
+        for (int j = 0; j < COLS; ++j)
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            hwin[rr][j][k] = fmaf(kv[3], q[j + 3][k], fmaf(kv[2], q[j + 2][k], fmaf(kv[1], q[j + 1][k], kv[0] * q[j][k])));
       } else {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) rw[rr][i] = q[i];
+        for (int i = 0; i < COLS + 3; ++i)
+#pragma unroll
+          for (int k = 0; k < V; ++k) rwin[rr][i][k] = q[i][k];
       }
       const int ro = r_in - 3;             // output row (relative to oy0) completed by this input row
       if (ro >= 0 && ro < rows_out) {
         const int oy = oy0 + ro;
-        float4 acc[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < COLS; ++j) {
+          float a4[V];
           if constexpr (SEP) {
-            if (FUSED) {                   // accumulate straight into row_scale*t + bias + noise (all x gain if `fast`)
-              const float nzj = nw * nzc[rr][j];
-              a4 = make_float4(bq.x + nzj, bq.y + nzj, bq.z + nzj, bq.w + nzj);
-            }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const float4 h = hw[(rr + 1 + a) & 3][j];   // rows r_in-3 .. r_in in order
-              if (FUSED) {
-                a4.x = fmaf(kur[a].x, h.x, a4.x); a4.y = fmaf(kur[a].y, h.y, a4.y);
-                a4.z = fmaf(kur[a].z, h.z, a4.z); a4.w = fmaf(kur[a].w, h.w, a4.w);
-              } else {
-                a4.x = fmaf(ku[a], h.x, a4.x); a4.y = fmaf(ku[a], h.y, a4.y);
-                a4.z = fmaf(ku[a], h.z, a4.z); a4.w = fmaf(ku[a], h.w, a4.w);
-              }
+            for (int k = 0; k < V; ++k) {
+              const float h0 = hwin[(rr + 1) & 3][j][k], h1 = hwin[(rr + 2) & 3][j][k];
+              const float h2 = hwin[(rr + 3) & 3][j][k], h3 = hwin[rr][j][k];       // rows r_in-3 .. r_in in order
+              a4[k] = fmaf(ku[3], h3, fmaf(ku[2], h2, fmaf(ku[1], h1, ku[0] * h0)));
             }
           } else {
 #pragma unroll
+            for (int k = 0; k < V; ++k) a4[k] = 0.f;
+#pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                const float4 v = rw[(rr + 1 + a) & 3][j + b];
-                a4.x = fmaf(kf[a][b], v.x, a4.x); a4.y = fmaf(kf[a][b], v.y, a4.y);
-                a4.z = fmaf(kf[a][b], v.z, a4.z); a4.w = fmaf(kf[a][b], v.w, a4.w);
-              }
-            if (FUSED) {
-              const float nzj = nw * nzc[rr][j];
-              a4.x = fmaf(a4.x, rq.x, bq.x + nzj); a4.y = fmaf(a4.y, rq.y, bq.y + nzj);
-              a4.z = fmaf(a4.z, rq.z, bq.z + nzj); a4.w = fmaf(a4.w, rq.w, bq.w + nzj);
-            }
+              for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int k = 0; k < V; ++k) a4[k] = fmaf(kf[a][b], rwin[(rr + 1 + a) & 3][j + b][k], a4[k]);
           }
+          const int64_t ooff = (((static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + xo + j) * p.c + c0) + cq * V;
           if (FUSED) {
-            if (fast) {
-              a4.x = fmaxf(a4.x, a4.x * neg); a4.y = fmaxf(a4.y, a4.y * neg);
-              a4.z = fmaxf(a4.z, a4.z * neg); a4.w = fmaxf(a4.w, a4.w * neg);
-            } else {
-              a4.x = (a4.x > 0.f ? a4.x : a4.x * neg) * p.gain; a4.y = (a4.y > 0.f ? a4.y : a4.y * neg) * p.gain;
-              a4.z = (a4.z > 0.f ? a4.z : a4.z * neg) * p.gain; a4.w = (a4.w > 0.f ? a4.w : a4.w * neg) * p.gain;
+            const float nzj = nw * nzc[rr][j];
+            float o2[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              float t = fmaf(a4[k], rq[k], bq[k] + nzj);
+              t = fast ? fmaxf(t, t * neg) : (t > 0.f ? t : t * neg) * p.gain;
+              a4[k] = t;
+              o2[k] = t * sq[k];
             }
+            if (okc[j]) {
+              if (out) *reinterpret_cast<uint4*>(out + ooff) = ChanVec<T>::pack(a4);
+              if (out2) *reinterpret_cast<uint4*>(out2 + ooff) = ChanVec<T>::pack(o2);
+            }
+          } else if (MODE == 2) {
+            if (okc[j]) {
+              if (mul) {
+                float mf[V];
+                ChanVec<T>::unpack(__ldg(reinterpret_cast<const uint4*>(mul + ooff)), mf);
+#pragma unroll
+                for (int k = 0; k < V; ++k) dacc[k] = fmaf(a4[k], mf[k], dacc[k]);
+              }
+#pragma unroll
+              for (int k = 0; k < V; ++k) a4[k] *= rq[k];
+              *reinterpret_cast<uint4*>(out + ooff) = ChanVec<T>::pack(a4);
+            }
+          } else {
+            if (okc[j]) *reinterpret_cast<uint4*>(out + ooff) = ChanVec<T>::pack(a4);
           }
-          acc[j] = a4;
         }
-        float* op = out + (((static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + xo) * p.c + c0) + cq * 4;
-        if (ok0) *reinterpret_cast<float4*>(op) = acc[0];
-        if (ok1) *reinterpret_cast<float4*>(op + p.c) = acc[1];
       }
     }
     __syncthreads();   // the stage is free for the producer
+  }
+  if (MODE == 2 && partial) {
+    // sum over the 32 column groups of the CTA: [xg][CB] in the (now idle) first stage, then one row per CTA at
+    // partial[n][bx * gridDim.y + seg][C] (summed over the middle index by nhwc_finish_kernel)
+    float* red = reinterpret_cast<float*>(tiles_raw);
+#pragma unroll
+    for (int k = 0; k < V; ++k) red[xg * CB + cq * V + k] = dacc[k];
+    __syncthreads();
+    if (tid < CB) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int g = 0; g < 32; ++g) t += red[g * CB + tid];
+      const int64_t K = static_cast<int64_t>(gridDim.x / chunks) * gridDim.y;
+      const int64_t kidx = static_cast<int64_t>(bx) * gridDim.y + blockIdx.y;
+      partial[(static_cast<int64_t>(n) * K + kidx) * p.c + c0 + tid] = t;
+    }
   }
 }
 
@@ -571,26 +609,39 @@ using namespace gg;
 
 extern "C" {
 
-int gg_noise_bias_act_nhwc(float* out, const float* x, const float* noise, const float* noise_weight, const float* bias,
-                           const float* row_scale, float alpha, float scale, int64_t N, int C, int64_t HW, void* stream) {
+#define GG_DISPATCH_T(dtype_, who_, ...)                                                                   \
+  switch (dtype_) {                                                                                        \
+    case GG_F32: { using T_ = float; __VA_ARGS__; break; }                                                 \
+    case GG_BF16: { using T_ = __nv_bfloat16; __VA_ARGS__; break; }                                        \
+    default: return fail(GG_ERR_UNSUPPORTED, "%s: dtype %d not supported (fp32 or bf16)", who_, dtype_);  \
+  }
+
+static inline int vec_of(int dtype) { return dtype == GG_BF16 ? 8 : 4; }
+
+int gg_noise_bias_act_nhwc(void* out, const void* x, const float* noise, const float* noise_weight, const float* bias,
+                           const float* row_scale, int dtype, float alpha, float scale, int64_t N, int C, int64_t HW,
+                           void* stream) {
   if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "noise_bias_act_nhwc: negative size");
+  if (dtype != GG_F32 && dtype != GG_BF16) return fail(GG_ERR_UNSUPPORTED, "noise_bias_act_nhwc: dtype %d not supported", dtype);
   const int64_t numel = N * HW * C;
   if (numel == 0) return GG_OK;
-  if (C % 4 != 0) return fail(GG_ERR_UNSUPPORTED, "noise_bias_act_nhwc: C must be a multiple of 4");
+  const int V = vec_of(dtype);
+  if (C % V != 0) return fail(GG_ERR_UNSUPPORTED, "noise_bias_act_nhwc: C must be a multiple of %d", V);
   if (!out || !x) return fail(GG_ERR_BAD_ARG, "noise_bias_act_nhwc: null tensor");
-  const int64_t n_vec = numel / 4;
+  const int64_t n_vec = numel / V;
   const int64_t grid = (n_vec + 4 * kT - 1) / (4 * kT);
   if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "noise_bias_act_nhwc: tensor too large");
-  noise_bias_act_nhwc_kernel<<<static_cast<unsigned>(grid), kT, 0, static_cast<cudaStream_t>(stream)>>>(
-      out, x, noise, noise_weight, bias, row_scale, alpha, scale, n_vec, C / 4, HW);
+  GG_DISPATCH_T(dtype, "noise_bias_act_nhwc",
+                (noise_bias_act_nhwc_kernel<T_><<<static_cast<unsigned>(grid), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+                    static_cast<T_*>(out), static_cast<const T_*>(x), noise, noise_weight, bias, row_scale, alpha, scale,
+                    n_vec, C / V, HW)));
   GG_CHECK_LAUNCH("noise_bias_act_nhwc launch");
   return GG_OK;
 }
 
 // Pixels per CTA: enough CTAs to fill the machine ~8x over, at least 4 trips of the CTA's pixel lanes each.
-static int64_t rowwise_chunk(int64_t N, int C, int64_t HW) {
-  const int c4 = C / 4;
-  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;
+static int64_t rowwise_chunk(int64_t N, int cv, int64_t HW) {
+  const int lanes_p = kT / cv > 0 ? kT / cv : 1;
   const int64_t target = 8LL * sm_count();
   int64_t k = (target + N - 1) / N;
   const int64_t kmax = (HW + 4 * lanes_p - 1) / (4 * lanes_p);
@@ -601,33 +652,44 @@ static int64_t rowwise_chunk(int64_t N, int C, int64_t HW) {
 
 int64_t gg_nhwc_rowwise_workspace(int64_t N, int C, int64_t HW) {
   if (N <= 0 || C <= 0 || HW <= 0 || C % 4 != 0) return 0;
-  const int64_t chunk = rowwise_chunk(N, C, HW);
-  return N * ((HW + chunk - 1) / chunk) * C * static_cast<int64_t>(sizeof(float));
+  // the fp32 geometry has the most CTAs (4 channels per thread): sized for either storage type
+  const int64_t chunk = rowwise_chunk(N, C / 4, HW);
+  const int64_t chunk8 = (C % 8 == 0) ? rowwise_chunk(N, C / 8, HW) : chunk;
+  const int64_t k = (HW + (chunk < chunk8 ? chunk : chunk8) - 1) / (chunk < chunk8 ? chunk : chunk8);
+  return N * k * C * static_cast<int64_t>(sizeof(float));
 }
 
-static int launch_rowwise(int mode, float* out, float* dst, void* workspace, const float* x, const float* y, const float* s,
-                          float alpha, float gain, int64_t N, int C, int64_t HW, bool per_sample, void* stream) {
+static int launch_rowwise(int mode, void* out, float* dst, void* workspace, const void* x, const void* y, const float* s,
+                          int dtype, float alpha, float gain, int64_t N, int C, int64_t HW, bool per_sample, void* stream) {
   if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: negative size");
+  if (dtype != GG_F32 && dtype != GG_BF16) return fail(GG_ERR_UNSUPPORTED, "nhwc rowwise: dtype %d not supported", dtype);
   if (N * HW * C == 0) return GG_OK;
-  if (C % 4 != 0 || C > 1024) return fail(GG_ERR_UNSUPPORTED, "nhwc rowwise: C must be a multiple of 4 and <= 1024");
+  const int V = vec_of(dtype);
+  if (C % V != 0 || C / V > kT) return fail(GG_ERR_UNSUPPORTED, "nhwc rowwise: C must be a multiple of %d and <= %d", V, V * kT);
   if (!out || !x) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: null tensor");
   if (dst && !workspace) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: reduction needs a workspace");
-  const int c4 = C / 4;
-  const int64_t chunk64 = rowwise_chunk(N, C, HW);
+  const int cv = C / V;
+  const int64_t chunk64 = rowwise_chunk(N, cv, HW);
   if (chunk64 > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: plane too large");
   const int chunk = static_cast<int>(chunk64);
   const int K = static_cast<int>((HW + chunk - 1) / chunk);
   const int64_t grid = N * K;
   if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "nhwc rowwise: too many CTAs");
-  const int lanes_p = kT / c4 > 0 ? kT / c4 : 1;
+  const int lanes_p = kT / cv > 0 ? kT / cv : 1;
   const size_t smem = static_cast<size_t>(lanes_p) * C * sizeof(float);
   float* partial = dst ? static_cast<float*>(workspace) : nullptr;
   auto st = static_cast<cudaStream_t>(stream);
-  if (mode == 0)
-    rowwise_nhwc_kernel<0><<<static_cast<unsigned>(grid), kT, smem, st>>>(out, partial, x, dst ? y : nullptr, s, alpha, gain,
-                                                                         c4, HW, chunk, K);
-  else
-    rowwise_nhwc_kernel<1><<<static_cast<unsigned>(grid), kT, smem, st>>>(out, partial, x, y, s, alpha, gain, c4, HW, chunk, K);
+  const unsigned g = static_cast<unsigned>(grid);
+  if (mode == 0) {
+    GG_DISPATCH_T(dtype, "nhwc rowwise",
+                  (rowwise_nhwc_kernel<T_, 0><<<g, kT, smem, st>>>(static_cast<T_*>(out), partial, static_cast<const T_*>(x),
+                                                                 dst ? static_cast<const T_*>(y) : nullptr, s, alpha, gain,
+                                                                 cv, HW, chunk, K)));
+  } else {
+    GG_DISPATCH_T(dtype, "nhwc rowwise",
+                  (rowwise_nhwc_kernel<T_, 1><<<g, kT, smem, st>>>(static_cast<T_*>(out), partial, static_cast<const T_*>(x),
+                                                                 static_cast<const T_*>(y), s, alpha, gain, cv, HW, chunk, K)));
+  }
   GG_CHECK_LAUNCH("nhwc rowwise launch");
   if (dst) {
     const int64_t rows = per_sample ? N : 1;
@@ -638,17 +700,17 @@ static int launch_rowwise(int mode, float* out, float* dst, void* workspace, con
   return GG_OK;
 }
 
-int gg_channel_scale_nhwc(float* out, float* row_dot, void* workspace, const float* x, const float* y, const float* s,
-                          int64_t N, int C, int64_t HW, void* stream) {
+int gg_channel_scale_nhwc(void* out, float* row_dot, void* workspace, const void* x, const void* y, const float* s,
+                          int dtype, int64_t N, int C, int64_t HW, void* stream) {
   if (!s) return fail(GG_ERR_BAD_ARG, "channel_scale_nhwc: null scale");
   if (row_dot && !y) return fail(GG_ERR_BAD_ARG, "channel_scale_nhwc: row_dot needs y");
-  return launch_rowwise(0, out, row_dot, workspace, x, y, s, 0.f, 1.f, N, C, HW, true, stream);
+  return launch_rowwise(0, out, row_dot, workspace, x, y, s, dtype, 0.f, 1.f, N, C, HW, true, stream);
 }
 
-int gg_bias_act_backward_nhwc(float* gx, float* grad_bias, void* workspace, const float* g, const float* out_saved,
-                              float alpha, float scale, int64_t N, int C, int64_t HW, void* stream) {
+int gg_bias_act_backward_nhwc(void* gx, float* grad_bias, void* workspace, const void* g, const void* out_saved,
+                              int dtype, float alpha, float scale, int64_t N, int C, int64_t HW, void* stream) {
   if (!out_saved) return fail(GG_ERR_BAD_ARG, "bias_act_backward_nhwc: null saved output");
-  return launch_rowwise(1, gx, grad_bias, workspace, g, out_saved, nullptr, alpha, scale, N, C, HW, false, stream);
+  return launch_rowwise(1, gx, grad_bias, workspace, g, out_saved, nullptr, dtype, alpha, scale, N, C, HW, false, stream);
 }
 
 int64_t gg_to_rgb_nhwc_workspace(int64_t N, int C, int64_t HW) { return 3 * gg_nhwc_rowwise_workspace(N, C, HW); }
@@ -684,7 +746,7 @@ int gg_to_rgb_nhwc_backward(float* gx, float* gwm, void* workspace, const float*
   if (!g || !wm || (!gx && !gwm)) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: null tensor");
   if (gwm && (!x || !workspace)) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: gwm needs x and a workspace");
   const int c4 = C / 4;
-  const int64_t chunk64 = rowwise_chunk(N, C, HW);
+  const int64_t chunk64 = rowwise_chunk(N, c4, HW);
   if (chunk64 > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "to_rgb_nhwc backward: plane too large");
   const int chunk = static_cast<int>(chunk64);
   const int K = static_cast<int>((HW + chunk - 1) / chunk);
@@ -703,67 +765,144 @@ int gg_to_rgb_nhwc_backward(float* gx, float* gwm, void* workspace, const float*
   return GG_OK;
 }
 
-int gg_blur_nhwc(float* out, const float* in, const float* kernel, const float* noise, const float* noise_weight,
-                 const float* bias, const float* row_scale, int64_t N, int C, int in_h, int in_w, int kernel_h,
-                 int kernel_w, int separable, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int fused, int act,
-                 float alpha, float scale, void* stream) {
-  if (N < 0 || C < 0 || in_h < 1 || in_w < 1) return fail(GG_ERR_BAD_ARG, "blur_nhwc: bad shape");
-  if (kernel_h < 1 || kernel_w < 1 || kernel_h > 4 || kernel_w > 4) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: filter must be <= 4x4");
-  if (C % kCB != 0) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: C must be a multiple of %d", kCB);
-  if (act != 1 && act != 3) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: act must be 1 or 3");
-  const int out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
-  const int out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
-  if (out_h < 1 || out_w < 1) return fail(GG_ERR_BAD_ARG, "blur_nhwc: empty output");
-  if (N == 0 || C == 0) return GG_OK;
-  if (!out || !in || !kernel) return fail(GG_ERR_BAD_ARG, "blur_nhwc: null tensor");
-  if (N > 65535) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: batch > 65535");
+// ---- blur: geometry shared by the launch and the workspace query
+struct BlurPlan {
+  int out_h, out_w, xblocks, chunks, segs, seg_rows;
+};
+static int blur_plan(BlurPlan* pl, int dtype, int64_t N, int C, int in_h, int in_w, int kernel_h, int kernel_w, int pad_x0,
+                     int pad_x1, int pad_y0, int pad_y1) {
+  const int V = vec_of(dtype);
+  const int CB = 8 * V, BX = (V == 4) ? 64 : 32;
+  if (C % CB != 0) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: C must be a multiple of %d", CB);
+  pl->out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
+  pl->out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
+  if (pl->out_h < 1 || pl->out_w < 1) return fail(GG_ERR_BAD_ARG, "blur_nhwc: empty output");
+  pl->xblocks = (pl->out_w + BX - 1) / BX;
+  pl->chunks = C / CB;
+  // row segments: enough CTAs to fill the machine twice, at least 16 rows each (3 halo rows per segment)
+  const int64_t base_ctas = static_cast<int64_t>(pl->xblocks) * pl->chunks * (N > 0 ? N : 1);
+  int segs = static_cast<int>((2LL * 2 * sm_count() + base_ctas - 1) / base_ctas);
+  int seg_rows = (pl->out_h + segs - 1) / segs;
+  if (seg_rows < 16) seg_rows = pl->out_h < 16 ? pl->out_h : 16;
+  seg_rows = (seg_rows + 3) / 4 * 4;
+  pl->seg_rows = seg_rows;
+  pl->segs = (pl->out_h + seg_rows - 1) / seg_rows;
+  return GG_OK;
+}
+
+int64_t gg_blur_nhwc_workspace(int dtype, int64_t N, int C, int in_h, int in_w, int kernel_h, int kernel_w, int pad_x0,
+                               int pad_x1, int pad_y0, int pad_y1) {
+  BlurPlan pl;
+  if (N <= 0 || C <= 0 || (dtype != GG_F32 && dtype != GG_BF16)) return 0;
+  if (blur_plan(&pl, dtype, N, C, in_h, in_w, kernel_h, kernel_w, pad_x0, pad_x1, pad_y0, pad_y1) != GG_OK) return 0;
+  return N * static_cast<int64_t>(pl.xblocks) * pl.segs * C * static_cast<int64_t>(sizeof(float));
+}
+
+}  // extern "C"
+
+template <typename T>
+static int launch_blur(void* out, void* out2, const void* in, const float* kernel, const float* noise,
+                       const float* noise_weight, const float* bias, const float* row_scale, const float* scale2,
+                       const void* mul, float* row_dot, void* workspace, int64_t N, int C, int in_h, int in_w, int kernel_h,
+                       int kernel_w, int separable, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int mode, int act,
+                       float alpha, float scale, void* stream, int dtype) {
+  using G = BlurGeom<T>;
+  BlurPlan pl;
+  int rc = blur_plan(&pl, dtype, N, C, in_h, in_w, kernel_h, kernel_w, pad_x0, pad_x1, pad_y0, pad_y1);
+  if (rc != GG_OK) return rc;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(GG_ERR_CUDA, "blur_nhwc: cuTensorMapEncodeTiled is not available from this driver");
+  // descriptors are memoised per (address, shape, type): a training loop (or a captured graph's warm-up) presents the
+  // same few activations again and again
+  struct MapKey { const void* ptr; int64_t n; int c, h, w, es; };
+  struct MapEnt { MapKey key; CUtensorMap map; bool valid; };
+  static thread_local MapEnt cache[16] = {};
+  static thread_local unsigned cache_next = 0;
+  const MapKey key = {in, N, C, in_h, in_w, static_cast<int>(sizeof(T))};
+  const CUtensorMap* cached = nullptr;
+  for (int i = 0; i < 16 && !cached; ++i)
+    if (cache[i].valid && cache[i].key.ptr == key.ptr && cache[i].key.n == key.n && cache[i].key.c == key.c &&
+        cache[i].key.h == key.h && cache[i].key.w == key.w && cache[i].key.es == key.es)
+      cached = &cache[i].map;
   CUtensorMap tmap;
+  if (cached) tmap = *cached;
+  const cuuint64_t es = sizeof(T);
   const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(in_w), static_cast<cuuint64_t>(in_h),
                               static_cast<cuuint64_t>(N)};
-  const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(in_w) * C * 4,
-                              static_cast<cuuint64_t>(in_h) * in_w * C * 4};
-  const cuuint32_t box[4] = {kCB, kTileW, kRY, 1};
+  const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * es, static_cast<cuuint64_t>(in_w) * C * es,
+                              static_cast<cuuint64_t>(in_h) * in_w * C * es};
+  const cuuint32_t box[4] = {G::CB, G::TW, kRY, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(GG_ERR_CUDA, "blur_nhwc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  if (!cached) {
+    const CUresult r = enc(&tmap, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                           const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GG_ERR_CUDA, "blur_nhwc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    MapEnt& e = cache[cache_next++ % 16];
+    e.key = key; e.map = tmap; e.valid = true;
+  }
   BlurNhwcParams p;
-  p.n = static_cast<int>(N); p.c = C; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
+  p.n = static_cast<int>(N); p.c = C; p.in_h = in_h; p.in_w = in_w; p.out_h = pl.out_h; p.out_w = pl.out_w;
   p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
   p.act = act; p.alpha = alpha; p.gain = scale;
-  // row segments: enough CTAs to fill the machine twice, at least 16 rows each (3 halo rows per segment)
-  const int xblocks = (out_w + kBX - 1) / kBX;
-  const int64_t base_ctas = static_cast<int64_t>(xblocks) * (C / kCB) * N;
-  int segs = static_cast<int>((2LL * 2 * sm_count() + base_ctas - 1) / base_ctas);
-  int seg_rows = (out_h + segs - 1) / segs;
-  if (seg_rows < 16) seg_rows = out_h < 16 ? out_h : 16;
-  seg_rows = (seg_rows + 3) / 4 * 4;
-  p.seg_rows = seg_rows;
-  const dim3 grid(static_cast<unsigned>(xblocks * (C / kCB)), static_cast<unsigned>((out_h + seg_rows - 1) / seg_rows),
-                  static_cast<unsigned>(N));
-  const size_t smem = static_cast<size_t>(kNS) * kStageFloats * sizeof(float);
+  p.seg_rows = pl.seg_rows;
+  const dim3 grid(static_cast<unsigned>(pl.xblocks * pl.chunks), static_cast<unsigned>(pl.segs), static_cast<unsigned>(N));
+  const size_t smem = static_cast<size_t>(kNS) * G::STAGE_ELEMS * sizeof(T);
   static DeviceOnce configured;
   if (configured.needed()) {
     cudaError_t e = cudaSuccess;
-    const void* kernels[4] = {reinterpret_cast<const void*>(blur_nhwc_kernel<true, true>),
-                              reinterpret_cast<const void*>(blur_nhwc_kernel<true, false>),
-                              reinterpret_cast<const void*>(blur_nhwc_kernel<false, true>),
-                              reinterpret_cast<const void*>(blur_nhwc_kernel<false, false>)};
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+    const void* kernels[6] = {reinterpret_cast<const void*>(blur_nhwc_kernel<T, 0, true>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 0, false>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, true>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, false>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 2, true>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 2, false>)};
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_fail(e, "blur_nhwc smem opt-in");
     configured.done();
   }
   auto st = static_cast<cudaStream_t>(stream);
-#define GG_BLUR(F_, S_) blur_nhwc_kernel<F_, S_><<<grid, kT, smem, st>>>(out, tmap, kernel, kernel_h, kernel_w, noise, noise_weight, bias, row_scale, p)
-  if (fused) { if (separable) GG_BLUR(true, true); else GG_BLUR(true, false); }
-  else { noise = nullptr; noise_weight = nullptr; bias = nullptr; row_scale = nullptr;
-         if (separable) GG_BLUR(false, true); else GG_BLUR(false, false); }
+  float* partial = (mode == 2 && row_dot) ? static_cast<float*>(workspace) : nullptr;
+#define GG_BLUR(M_, S_)                                                                                              \
+  blur_nhwc_kernel<T, M_, S_><<<grid, kT, smem, st>>>(static_cast<T*>(out), static_cast<T*>(out2), tmap, kernel, kernel_h,  \
+                                                     kernel_w, noise, noise_weight, bias, row_scale, scale2,         \
+                                                     static_cast<const T*>(mul), partial, p)
+  if (mode == 1) { if (separable) GG_BLUR(1, true); else GG_BLUR(1, false); }
+  else if (mode == 2) { if (separable) GG_BLUR(2, true); else GG_BLUR(2, false); }
+  else { if (separable) GG_BLUR(0, true); else GG_BLUR(0, false); }
 #undef GG_BLUR
   GG_CHECK_LAUNCH("blur_nhwc launch");
+  if (partial) {
+    const int K = pl.xblocks * pl.segs;
+    nhwc_finish_kernel<<<static_cast<unsigned>(N * ((C + 31) / 32)), dim3(32, 32), 0, st>>>(row_dot, partial, N, K, C);
+    GG_CHECK_LAUNCH("blur_nhwc finish launch");
+  }
+  return GG_OK;
+}
+
+extern "C" {
+
+int gg_blur_nhwc(void* out, void* out2, const void* in, const float* kernel, const float* noise, const float* noise_weight,
+                 const float* bias, const float* row_scale, const float* scale2, const void* mul, float* row_dot,
+                 void* workspace, int dtype, int64_t N, int C, int in_h, int in_w, int kernel_h, int kernel_w, int separable,
+                 int pad_x0, int pad_x1, int pad_y0, int pad_y1, int mode, int act, float alpha, float scale, void* stream) {
+  if (N < 0 || C < 0 || in_h < 1 || in_w < 1) return fail(GG_ERR_BAD_ARG, "blur_nhwc: bad shape");
+  if (kernel_h < 1 || kernel_w < 1 || kernel_h > 4 || kernel_w > 4) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: filter must be <= 4x4");
+  if (mode < 0 || mode > 2) return fail(GG_ERR_BAD_ARG, "blur_nhwc: mode must be 0 (blur), 1 (fused tail) or 2 (adjoint epilogue)");
+  if (act != 1 && act != 3) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: act must be 1 or 3");
+  if (dtype != GG_F32 && dtype != GG_BF16) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: dtype %d not supported (fp32 or bf16)", dtype);
+  if (N == 0 || C == 0) return GG_OK;
+  if (!in || !kernel) return fail(GG_ERR_BAD_ARG, "blur_nhwc: null tensor");
+  if (mode == 1 ? (!out && !out2) : !out) return fail(GG_ERR_BAD_ARG, "blur_nhwc: null output");
+  if (mode != 1 && out2) return fail(GG_ERR_BAD_ARG, "blur_nhwc: out2 belongs to the fused tail (mode 1)");
+  if (mode == 2 && row_dot && (!mul || !workspace)) return fail(GG_ERR_BAD_ARG, "blur_nhwc: row_dot needs `mul` and a workspace");
+  if (N > 65535) return fail(GG_ERR_UNSUPPORTED, "blur_nhwc: batch > 65535");
+  if (mode == 0) { noise = nullptr; noise_weight = nullptr; bias = nullptr; row_scale = nullptr; scale2 = nullptr; }
+  GG_DISPATCH_T(dtype, "blur_nhwc",
+                return launch_blur<T_>(out, out2, in, kernel, noise, noise_weight, bias, row_scale, scale2, mul, row_dot,
+                                       workspace, N, C, in_h, in_w, kernel_h, kernel_w, separable, pad_x0, pad_x1, pad_y0,
+                                       pad_y1, mode, act, alpha, scale, stream, dtype));
   return GG_OK;
 }
 

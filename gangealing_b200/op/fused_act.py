@@ -45,19 +45,13 @@ def fused_bias_act_raw(x, bias, ref, act, grad, alpha, scale):
 def bias_act_backward_raw(grad_output, out, alpha, scale, want_bias_grad):
     """gx = (out > 0 ? g : alpha*g)*scale and, optionally, grad_bias = gx.sum(all dims but 1) (fp32)."""
     _lib.require_cuda(grad_output, out)
-    if _lib.is_nhwc(out) and out.shape[1] % 4 == 0 and out.shape[1] <= 1024 and grad_output.shape == out.shape:
+    if (_lib.is_nhwc(out) and out.shape[1] % _lib.nhwc_vec(out) == 0 and out.shape[1] // _lib.nhwc_vec(out) <= 256
+            and grad_output.shape == out.shape):
+        from . import nhwc
         g = grad_output.contiguous(memory_format=torch.channels_last)
-        n, c, h, w = out.shape
-        lib = _lib.load()
-        gx = torch.empty_like(out)
-        grad_bias = ws = None
-        if want_bias_grad:
-            grad_bias = torch.empty(c, dtype=torch.float32, device=g.device)
-            ws = torch.empty(max(1, lib.gg_nhwc_rowwise_workspace(n, c, h * w) // 4), dtype=torch.float32, device=g.device)
-        rc = lib.gg_bias_act_backward_nhwc(gx.data_ptr(), _lib.ptr(grad_bias), _lib.ptr(ws), g.data_ptr(), out.data_ptr(),
-                                           alpha, scale, n, c, h * w, _lib.stream())
-        _lib.check(rc, "gg_bias_act_backward_nhwc")
-        return gx, grad_bias
+        if g.dtype != out.dtype:
+            g = g.to(out.dtype)
+        return nhwc.bias_act_backward(g, out, alpha, scale, want_bias_grad)
     g = grad_output.contiguous()
     out = out.contiguous()
     if g.shape != out.shape or g.dtype != out.dtype:
@@ -104,7 +98,16 @@ class _FusedLeakyReLUGrad(Function):
 class FusedLeakyReLUFunction(Function):
     @staticmethod
     def forward(ctx, input, bias, negative_slope, scale):
-        out = fused_bias_act_raw(input, bias, None, 3, 0, negative_slope, scale)
+        _lib.require_cuda(input, bias)
+        if (_lib.is_nhwc(input) and input.shape[1] % _lib.nhwc_vec(input) == 0
+                and (bias is None or bias.numel() in (0, input.shape[1]))):
+            # channels-last: the 16-byte-vector streaming kernel of csrc/nhwc.cu (100 % of the HBM peak; the flat
+            # kernel's per-element `i % C` bias indexing reached 41 %: profiles/r02_opbench_vs_reference_b32_before.txt)
+            from . import nhwc
+            b = bias if (bias is not None and bias.numel() > 0) else None
+            out = nhwc.noise_bias_act(input, None, None, b, None, negative_slope, scale)
+        else:
+            out = fused_bias_act_raw(input, bias, None, 3, 0, negative_slope, scale)
         ctx.save_for_backward(out)
         ctx.cfg = (negative_slope, scale)
         return out

@@ -18,22 +18,13 @@ from .. import _lib
 def channel_scale_raw(x, s, y=None):
     """out = x * s[n, c]; with `y`: also row_dot[n, c] = sum_hw x*y (fp32).  x: (N, C, H, W); s: (N, C) fp32."""
     _lib.require_cuda(x, s, y)
-    if _lib.is_nhwc(x) and x.shape[1] % 4 == 0 and x.shape[1] <= 1024:
-        n, c, h, w = x.shape
-        s = s.reshape(n * c)
-        if s.dtype != torch.float32 or not s.is_contiguous():
-            s = s.float().contiguous()
-        lib = _lib.load()
-        out = torch.empty_like(x)
-        dot = ws = None
+    if _lib.is_nhwc(x) and x.shape[1] % _lib.nhwc_vec(x) == 0 and x.shape[1] // _lib.nhwc_vec(x) <= 256:
+        from . import nhwc
         if y is not None:
             y = y.contiguous(memory_format=torch.channels_last)
-            dot = torch.empty((n, c), dtype=torch.float32, device=x.device)
-            ws = torch.empty(max(1, lib.gg_nhwc_rowwise_workspace(n, c, h * w) // 4), dtype=torch.float32, device=x.device)
-        rc = lib.gg_channel_scale_nhwc(out.data_ptr(), _lib.ptr(dot), _lib.ptr(ws), x.data_ptr(), _lib.ptr(y), s.data_ptr(),
-                                       n, c, h * w, _lib.stream())
-        _lib.check(rc, "gg_channel_scale_nhwc")
-        return out, dot
+            if y.dtype != x.dtype:
+                y = y.to(x.dtype)
+        return nhwc.channel_scale(x, s, y)
     x = x.contiguous()
     n, c = x.shape[0], x.shape[1]
     hw = x.numel() // max(n * c, 1)
@@ -115,17 +106,18 @@ def demod_coefficients(weight, style, scale, eps=1e-8):
     return _Demod.apply(weight, style, float(scale), float(eps))
 
 
-def shared_conv_weight(weight, scale, transposed, channels_last=False):
-    """scale * W as the weight of a weight-SHARED convolution: (O, I, k, k), or (I, O, k, k) for conv_transpose2d.
-    Memoised on the parameter object for frozen filter banks."""
+def shared_conv_weight(weight, scale, transposed, channels_last=False, dtype=None):
+    """scale * W as the weight of a weight-SHARED convolution: (O, I, k, k), or (I, O, k, k) for conv_transpose2d, in
+    `dtype` (default: the parameter's).  Memoised on the parameter object for frozen filter banks."""
+    dtype = weight.dtype if dtype is None else dtype
     if weight.requires_grad:
-        w = weight[0] * scale
+        w = (weight[0] * scale).to(dtype)
         return w.transpose(0, 1) if transposed else w
     memo = _lib.tensor_cache(weight)
-    key = ("shared", float(scale), bool(transposed), bool(channels_last), weight.dtype)
+    key = ("shared", float(scale), bool(transposed), bool(channels_last), dtype)
     w = memo.get(key)
     if w is None:
-        w = (weight.detach()[0] * scale)
+        w = (weight.detach()[0] * scale).to(dtype)
         w = w.transpose(0, 1).contiguous() if transposed else w.contiguous()
         if channels_last and w.shape[2] * w.shape[3] > 1:
             w = w.contiguous(memory_format=torch.channels_last)
@@ -196,11 +188,11 @@ def modulated_conv2d(x, weight, style, scale, demodulate=True, upsample=False, p
             rgb = torch.bmm(wm.type(x.dtype), x.reshape(b, i, h * w_)).reshape(b, o, h, w_)
         return _epilogue(rgb, bias, skip), None
     xs = channel_scale(x, style)
-    w = shared_conv_weight(weight, scale, transposed=upsample, channels_last=_lib.is_nhwc(x))
+    w = shared_conv_weight(weight, scale, transposed=upsample, channels_last=_lib.is_nhwc(x), dtype=x.dtype)
     if upsample:
-        raw = conv2d_gradfix.conv_transpose2d(xs, w.type(x.dtype), padding=0, stride=2)
+        raw = conv2d_gradfix.conv_transpose2d(xs, w, padding=0, stride=2)
     else:
-        raw = conv2d_gradfix.conv2d(xs, w.type(x.dtype), padding=padding)
+        raw = conv2d_gradfix.conv2d(xs, w, padding=padding)
     d = demod_coefficients(weight, style, scale, eps) if demodulate else None
     return _epilogue(raw, bias, skip), d
 

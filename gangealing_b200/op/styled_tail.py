@@ -41,7 +41,8 @@ class _StyledTail(Function):
     @staticmethod
     def forward(ctx, x, noise, noise_weight, bias, kernel, pad, row_scale, negative_slope, scale):
         _lib.require_cuda(x, noise, noise_weight, bias, kernel, row_scale)
-        nhwc = _lib.is_nhwc(x) and x.shape[1] % (32 if kernel is not None else 4) == 0
+        vec = _lib.nhwc_vec(x) if x.dtype in (torch.float32, torch.bfloat16) else 4
+        nhwc = _lib.is_nhwc(x) and x.shape[1] % (8 * vec if kernel is not None else vec) == 0
         if not nhwc:
             x = x.contiguous()
         n, c, in_h, in_w = x.shape
@@ -50,30 +51,21 @@ class _StyledTail(Function):
         b = _f32(bias.reshape(-1)) if bias is not None else None
         rs = _f32(row_scale.reshape(-1)) if row_scale is not None else None
         if nhwc:
+            from . import nhwc as K
             if kernel is None:
-                out = torch.empty_like(x)
-                nz = _noise_plane(noise, x, in_h, in_w)
-                rc = lib.gg_noise_bias_act_nhwc(out.data_ptr(), x.data_ptr(), _lib.ptr(nz), _lib.ptr(nw), _lib.ptr(b),
-                                                _lib.ptr(rs), negative_slope, scale, n, c, in_h * in_w, _lib.stream())
-                _lib.check(rc, "gg_noise_bias_act_nhwc")
+                out = K.noise_bias_act(x, noise, nw, b, rs, negative_slope, scale)
             else:
-                taps = _taps(kernel)
-                kh, kw = taps.shape
-                out_h = in_h + pad[2] + pad[3] - kh + 1
-                out_w = in_w + pad[0] + pad[1] - kw + 1
-                out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-                nz = _noise_plane(noise, x, out_h, out_w)
                 if TIMING is not None:
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record()
-                rc = lib.gg_blur_nhwc(out.data_ptr(), x.data_ptr(), taps.data_ptr(), _lib.ptr(nz), _lib.ptr(nw), _lib.ptr(b),
-                                      _lib.ptr(rs), n, c, in_h, in_w, kh, kw, 1 if _lib.filter_is_separable(kernel) else 0,
-                                      pad[0], pad[1], pad[2], pad[3], 1, 3, negative_slope, scale, _lib.stream())
-                _lib.check(rc, "gg_blur_nhwc")
+                out = K.blur(x, kernel, pad, mode=1, noise=noise, noise_weight=nw, bias=b, row_scale=rs,
+                             negative_slope=negative_slope, gain=scale)[0]
                 if TIMING is not None:
                     ev1.record()
-                    TIMING.append((ev0, ev1, 4 * n * c * (in_h * in_w + out_h * out_w) + (4 * n * out_h * out_w if nz is not None else 0)
-                                   + 4 * (c + 1 + kh * kw)))
+                    es = x.element_size()
+                    kh, kw = kernel.shape
+                    TIMING.append((ev0, ev1, es * n * c * (in_h * in_w + out.shape[2] * out.shape[3])
+                                   + (4 * n * out.shape[2] * out.shape[3] if noise is not None else 0) + 4 * (c + 1 + kh * kw)))
         elif kernel is None:
             out = torch.empty_like(x)
             nz = _noise_plane(noise, x, in_h, in_w)

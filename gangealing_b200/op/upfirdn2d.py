@@ -38,14 +38,10 @@ def upfirdn2d_raw(x, kernel, up, down, pad):
     out_h, out_w = _out_size(in_h, in_w, kh, kw, up, down, pad)
     if out_h < 1 or out_w < 1:
         raise RuntimeError("upfirdn2d: empty output (%d x %d)" % (out_h, out_w))
-    if (_lib.is_nhwc(x) and c % 32 == 0 and up == (1, 1) and down == (1, 1) and kh <= 4 and kw <= 4):
-        # channels-last activations stay channels-last (TMA tensor-map kernel, csrc/nhwc.cu)
-        out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-        rc = _lib.load().gg_blur_nhwc(out.data_ptr(), x.data_ptr(), taps.data_ptr(), None, None, None, None, n, c, in_h,
-                                      in_w, kh, kw, 1 if _lib.filter_is_separable(kernel) else 0, pad[0], pad[1], pad[2],
-                                      pad[3], 0, 1, 0.0, 1.0, _lib.stream())
-        _lib.check(rc, "gg_blur_nhwc")
-        return out
+    if (_lib.is_nhwc(x) and c % (8 * _lib.nhwc_vec(x)) == 0 and up == (1, 1) and down == (1, 1) and kh <= 4 and kw <= 4):
+        # channels-last activations stay channels-last (TMA tensor-map kernel, csrc/nhwc.cu; fp32 or bf16 storage)
+        from . import nhwc
+        return nhwc.blur(x, kernel, pad, mode=0)[0]
     x = x.contiguous()
     out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device)
     rc = _lib.load().gg_upfirdn2d(out.data_ptr(), x.data_ptr(), taps.data_ptr(), _lib.dtype_code(x), n * c,

@@ -78,7 +78,12 @@ class EqualConv2d(nn.Module):
         self.ops = ops if ops is not None else cuda_ops()
 
     def forward(self, input):
-        return self.ops.conv2d(input, self.weight * self.scale, bias=self.bias, stride=self.stride, padding=self.padding)
+        w = self.weight * self.scale
+        b = self.bias
+        if w.dtype != input.dtype:      # bf16 activations (BASELINE config 3): fp32 master weights, bf16 tensor-core conv
+            w = w.to(input.dtype)
+            b = b.to(input.dtype) if b is not None else None
+        return self.ops.conv2d(input, w, bias=b, stride=self.stride, padding=self.padding)
 
     def __repr__(self):
         return (f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]},"
@@ -348,6 +353,13 @@ class Generator(nn.Module):
         # keep the synthesis activations channels-last (NHWC) between cuDNN's NHWC-native convolutions; the fused
         # kernels of this package have native channels-last variants (csrc/nhwc.cu).  Set by the Trainer on CUDA.
         self.channels_last = False
+        # storage type of the synthesis activations on the channels-last path: fp32 (BASELINE config 2) or bf16 (config 3:
+        # bf16 activations, fp32 arithmetic inside the fused kernels, bf16 tensor-core convolutions, fp32 RGB image)
+        self.act_dtype = torch.float32
+        self.fuse_synthesis = True      # cross-layer fused tails (op/styled_fused.py) when the configuration allows
+
+    def ops_are_native(self):
+        return getattr(self.conv1.ops, "name", None) == "sm_100a"
 
     def make_noise(self, batch_size=1):
         device = self.input.input.device
@@ -385,6 +397,11 @@ class Generator(nn.Module):
             latent = torch.cat([styles[0].unsqueeze(1).repeat(1, inject_index, 1),
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
 
+        if self.channels_last and self.fuse_synthesis and self.ops_are_native():
+            from ..op import styled_fused
+            if styled_fused.fusable(self, latent, self.act_dtype):
+                image = styled_fused.synthesis(self, latent, noise, self.act_dtype)
+                return (image, latent) if return_latents else (image, None)
         x0 = self.input(latent)
         if self.channels_last:
             x0 = x0.contiguous(memory_format=torch.channels_last)

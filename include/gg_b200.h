@@ -225,28 +225,66 @@ GG_API int gg_modconv_modulate(float* out, const float* weight, const float* sty
                                float scale, int B, int O, int I, int kk, int transposed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Channels-last (N, H, W, C; fp32; C % 4 == 0) variants of the StyledConv tail family.  Same math and reference
- * citations as gg_noise_bias_act / gg_bias_act_backward / gg_channel_scale / gg_blur_noise_bias_act; they exist so
- * the generator's activations can stay NHWC between cuDNN's (NHWC-native) tensor-core convolutions.
- *   gg_blur_nhwc: upfirdn2d(up = down = 1, filter <= 4x4) on (N, H, W, C), C % 32 == 0, input rows streamed with 4-D
- *     TMA tensor-map loads whose out-of-bounds zero fill is the padding; `separable` != 0 asserts a rank-1 filter
- *     (two 4-tap passes; the caller tests this once per filter); `fused` != 0 adds the tail
- *     lrelu(row_scale[n,c]*t + noise_weight*noise[n,y,x] + bias[c], alpha)*scale.
+ * Channels-last (N, H, W, C) variants of the StyledConv tail family.  Same math and reference citations as
+ * gg_noise_bias_act / gg_bias_act_backward / gg_channel_scale / gg_blur_noise_bias_act; they exist so the generator's
+ * activations can stay NHWC between cuDNN's (NHWC-native) tensor-core convolutions.
+ *   dtype: GG_F32 or GG_BF16 = the STORAGE type of the activations (arithmetic is fp32; BASELINE config 3 runs bf16
+ *     activations -- the reference has no bf16 at all: models/stylegan2/op/upfirdn2d_kernel.cu:311 dispatches
+ *     float/double/half only).  An activation moves 16 bytes at a time: C % 4 == 0 (fp32) / C % 8 == 0 (bf16).
+ *     noise, bias, row scales, reductions are always fp32.
+ *   gg_blur_nhwc: upfirdn2d(up = down = 1, filter <= 4x4) on (N, H, W, C), C % 32 == 0 (fp32) / C % 64 == 0 (bf16), input
+ *     rows streamed with 4-D TMA tensor-map loads whose out-of-bounds zero fill is the padding; `separable` != 0 asserts a
+ *     rank-1 filter (two 4-tap passes; the caller tests this once per filter).  mode:
+ *       0  out = B(in)                                                          (Blur, networks.py:70-86)
+ *       1  o = lrelu(row_scale[n,c]*B(in) + noise_weight*noise[n,y,x] + bias[c], alpha)*scale   (networks.py:266,291-298,346-348)
+ *          out = o (may be NULL) and/or out2 = o*scale2[n,c] (may be NULL): out2 is the NEXT modulated convolution's
+ *          input with its style modulation applied (networks.py:236,243), written by the pass that produces o
+ *       2  adjoint epilogue (backward of mode 1's blur): t = B(in); out = t*row_scale[n,c]; row_dot[n,c] = sum_yx t*mul[n,y,x,c]
+ *          (mul: same shape as out; NULL row_dot: no reduction) -- `workspace` of gg_blur_nhwc_workspace() bytes
  *   workspaces: gg_nhwc_rowwise_workspace(N, C, HW) bytes for the optional reductions (row_dot (N, C); grad_bias (C)).
  * ---------------------------------------------------------------------------------------------- */
-GG_API int gg_noise_bias_act_nhwc(float* out, const float* x, const float* noise, const float* noise_weight,
-                                  const float* bias, const float* row_scale, float alpha, float scale, int64_t N,
-                                  int C, int64_t HW, void* stream);
+GG_API int gg_noise_bias_act_nhwc(void* out, const void* x, const float* noise, const float* noise_weight,
+                                  const float* bias, const float* row_scale, int dtype, float alpha, float scale,
+                                  int64_t N, int C, int64_t HW, void* stream);
 GG_API int64_t gg_nhwc_rowwise_workspace(int64_t N, int C, int64_t HW);
-GG_API int gg_channel_scale_nhwc(float* out, float* row_dot, void* workspace, const float* x, const float* y,
-                                 const float* s, int64_t N, int C, int64_t HW, void* stream);
-GG_API int gg_bias_act_backward_nhwc(float* gx, float* grad_bias, void* workspace, const float* g,
-                                     const float* out_saved, float alpha, float scale, int64_t N, int C, int64_t HW,
-                                     void* stream);
-GG_API int gg_blur_nhwc(float* out, const float* in, const float* kernel, const float* noise,
-                        const float* noise_weight, const float* bias, const float* row_scale, int64_t N, int C,
-                        int in_h, int in_w, int kernel_h, int kernel_w, int separable, int pad_x0, int pad_x1,
-                        int pad_y0, int pad_y1, int fused, int act, float alpha, float scale, void* stream);
+GG_API int gg_channel_scale_nhwc(void* out, float* row_dot, void* workspace, const void* x, const void* y,
+                                 const float* s, int dtype, int64_t N, int C, int64_t HW, void* stream);
+GG_API int gg_bias_act_backward_nhwc(void* gx, float* grad_bias, void* workspace, const void* g,
+                                     const void* out_saved, int dtype, float alpha, float scale, int64_t N, int C,
+                                     int64_t HW, void* stream);
+GG_API int64_t gg_blur_nhwc_workspace(int dtype, int64_t N, int C, int in_h, int in_w, int kernel_h, int kernel_w,
+                                      int pad_x0, int pad_x1, int pad_y0, int pad_y1);
+GG_API int gg_blur_nhwc(void* out, void* out2, const void* in, const float* kernel, const float* noise,
+                        const float* noise_weight, const float* bias, const float* row_scale, const float* scale2,
+                        const void* mul, float* row_dot, void* workspace, int dtype, int64_t N, int C, int in_h,
+                        int in_w, int kernel_h, int kernel_w, int separable, int pad_x0, int pad_x1, int pad_y0,
+                        int pad_y1, int mode, int act, float alpha, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * StyledConv / ToRGB tails fused across layer boundaries (csrc/styled.cu), channels-last, dtype as above.
+ * reference: models/stylegan2/networks.py:291-298 (NoiseInjection), :346-348 (StyledConv.forward), :236,243 (the style
+ * modulation of the NEXT ModulatedConv2d, applied to its input here because conv(scale*W*s, x) == conv(scale*W, x*s)),
+ * :389-405 (ToRGB: 1x1 modulated convolution without demodulation + bias + up-sampled skip).
+ *   gg_styled_tail_nhwc:  o = act(demod[n,c]*raw + noise_weight*noise[n,p] + bias[c])*scale       raw: (N, HW, C)
+ *        out = o                         (NULL: not written -- only a later backward pass needs it)
+ *        xs  = o*s_next[n,c]             (NULL: not written)
+ *        rgb[n,o3,p] = sum_c wm[n,o3,c]*o + rgb_bias[o3] + skip[n,o3,p]    (NULL: not computed; planar (N, 3, HW) fp32)
+ *      C % 32 == 0 (fp32) / C % 64 == 0 (bf16).  One read of raw.
+ *   gg_styled_tail_backward_nhwc: one pass over (g_xs, out[, raw]) ->
+ *        g_o = g_xs*s_next + sum_o3 wm[n,o3,c]*g_rgb[n,o3,p];  g_t = act'(out)*scale*g_o;  g_raw = g_t*demod[n,c]
+ *        d_s_next[n,c] = sum_p g_xs*out;  d_demod[n,c] = sum_p g_t*raw;  d_wm[n,o3,c] = sum_p g_rgb[n,o3,p]*out
+ *      (each NULL: skipped; g_xs or g_rgb may be NULL; demod NULL: g_raw = g_t -- the blur layers apply demod in
+ *      gg_blur_nhwc mode 2).  `workspace`: gg_styled_tail_backward_workspace() bytes.  Deterministic reductions.
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int gg_styled_tail_nhwc(void* out, void* xs, float* rgb, const void* raw, const float* noise,
+                               const float* noise_weight, const float* bias, const float* demod, const float* s_next,
+                               const float* wm, const float* rgb_bias, const float* skip, int dtype, int act,
+                               float alpha, float scale, int64_t N, int C, int64_t HW, void* stream);
+GG_API int64_t gg_styled_tail_backward_workspace(int dtype, int64_t N, int C, int64_t HW);
+GG_API int gg_styled_tail_backward_nhwc(void* g_raw, float* d_s_next, float* d_demod, float* d_wm, void* workspace,
+                                        const void* g_xs, const float* g_rgb, const void* out_saved, const void* raw,
+                                        const float* s_next, const float* demod, const float* wm, int dtype,
+                                        float alpha, float scale, int64_t N, int C, int64_t HW, void* stream);
 
 /* to-RGB on channels-last activations (reference models/stylegan2/networks.py:389-405 `ToRGB.forward`: a 1x1 modulated
  * convolution without demodulation + bias + the up-sampled skip image; the reference builds B filter banks and runs a

@@ -67,10 +67,30 @@ def test_argument_validation_of_the_channels_last_and_loss_entry_points():
     # to-RGB and the NHWC family: channel-count contracts
     assert dll.gg_to_rgb_nhwc_forward(one, one, one, None, None, 1, 20, 16, None) == -2
     assert dll.gg_to_rgb_nhwc_backward(one, one, one, one, one, one, 1, 6, 16, None) == -2
-    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, one, 1, 6, 16, None) == -2
-    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, None, 1, 8, 16, None) == -1      # null scale
-    assert dll.gg_bias_act_backward_nhwc(one, None, None, one, None, 0.2, 1.0, 1, 8, 16, None) == -1  # null saved output
-    assert dll.gg_noise_bias_act_nhwc(one, one, None, None, None, None, 0.2, 1.0, 1, 6, 16, None) == -2
-    assert dll.gg_blur_nhwc(one, one, one, None, None, None, None, 1, 20, 8, 8, 4, 4, 1, 1, 1, 1, 1, 0, 1, 0.0, 1.0, None) == -2
-    assert dll.gg_blur_nhwc(one, one, one, None, None, None, None, 1, 32, 8, 8, 5, 5, 1, 1, 1, 1, 1, 0, 1, 0.0, 1.0, None) == -2
-    assert dll.gg_blur_nhwc(one, one, one, None, None, None, None, 1, 32, 8, 8, 4, 4, 1, 1, 1, 1, 1, 0, 2, 0.0, 1.0, None) == -2
+    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, one, 0, 1, 6, 16, None) == -2
+    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, one, 2, 1, 12, 16, None) == -2      # bf16: C % 8
+    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, one, 1, 1, 8, 16, None) == -2       # fp16: unsupported
+    assert dll.gg_channel_scale_nhwc(one, None, None, one, None, None, 0, 1, 8, 16, None) == -1      # null scale
+    assert dll.gg_bias_act_backward_nhwc(one, None, None, one, None, 0, 0.2, 1.0, 1, 8, 16, None) == -1  # null saved output
+    assert dll.gg_noise_bias_act_nhwc(one, one, None, None, None, None, 0, 0.2, 1.0, 1, 6, 16, None) == -2
+    blur_tail = [0, 1, 20, 8, 8, 4, 4, 1, 1, 1, 1, 1, 0, 1, 0.0, 1.0, None]   # dtype, N, C, h, w, kh, kw, sep, pads, mode, act, alpha, scale, stream
+    ptrs = [one, None, one, one] + [None] * 8
+    assert dll.gg_blur_nhwc(*ptrs, *blur_tail) == -2                                               # C % 32
+    assert dll.gg_blur_nhwc(*ptrs, 2, 1, 32, *blur_tail[3:]) == -2                                 # bf16: C % 64
+    assert dll.gg_blur_nhwc(*ptrs, 0, 1, 32, 8, 8, 5, 5, *blur_tail[7:]) == -2                     # filter > 4x4
+    assert dll.gg_blur_nhwc(*ptrs, 0, 1, 32, 8, 8, 4, 4, 1, 1, 1, 1, 1, 0, 2, 0.0, 1.0, None) == -2  # act
+    assert dll.gg_blur_nhwc(*ptrs, 0, 1, 32, 8, 8, 4, 4, 1, 1, 1, 1, 1, 3, 1, 0.0, 1.0, None) == -1  # mode
+    assert dll.gg_blur_nhwc(one, one, one, one, *([None] * 8), 0, 1, 32, 8, 8, 4, 4, 1, 1, 1, 1, 1, 0, 1, 0.0, 1.0, None) == -1  # out2 is mode 1's
+    assert dll.gg_blur_nhwc_workspace(0, 2, 64, 17, 17, 4, 4, 1, 1, 1, 1) > 0
+    # cross-layer fused tails
+    st = [None] * 8
+    assert dll.gg_styled_tail_nhwc(one, None, None, one, *st, 0, 3, 0.2, 1.0, 1, 20, 16, None) == -2     # C % 32
+    assert dll.gg_styled_tail_nhwc(one, None, None, one, *st, 2, 3, 0.2, 1.0, 1, 32, 16, None) == -2     # bf16: C % 64
+    assert dll.gg_styled_tail_nhwc(None, None, None, one, *st, 0, 3, 0.2, 1.0, 1, 32, 16, None) == -1    # nothing to write
+    assert dll.gg_styled_tail_nhwc(None, one, None, one, *st, 0, 3, 0.2, 1.0, 1, 32, 16, None) == -1     # xs without s_next
+    assert dll.gg_styled_tail_nhwc(one, None, None, one, *st, 0, 2, 0.2, 1.0, 1, 32, 16, None) == -2     # act
+    assert dll.gg_styled_tail_backward_nhwc(one, None, None, None, None, None, None, one, None, None, None, None,
+                                            0, 0.2, 1.0, 1, 32, 16, None) == -1                          # no upstream gradient
+    assert dll.gg_styled_tail_backward_nhwc(one, None, None, None, None, one, None, one, None, None, None, None,
+                                            0, 0.2, 1.0, 1, 32, 16, None) == -1                          # g_xs without s_next
+    assert dll.gg_styled_tail_backward_workspace(0, 2, 64, 256) > 0
