@@ -37,7 +37,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("GG_BENCH_BATCH", "32")), help="per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="single-GPU: run the step eagerly instead of as a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as a CUDA graph")
+    ap.add_argument("--dtype", default=os.environ.get("GG_BENCH_DTYPE", "f32"), choices=["f32", "bf16"],
+                    help="activation storage type: f32 = BASELINE config 2 (the headline), bf16 = config 3")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional config-3 (bf16) measurement of the default run")
     return ap.parse_args()
 
 
@@ -89,9 +92,13 @@ def phase(msg):
         print("[bench %7.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
 
 
-def workload_config(args):
-    return {"workload": "LSUN Cats 256^2 train.py step (StyleGAN2-256 generator + unimodal similarity+flow STN @128, "
-                        "perceptual VGG16 loss, Adam, EMA), synthetic latents + seeded random weights",
+WORKLOAD = ("LSUN Cats 256^2 train.py step (StyleGAN2-256 generator + unimodal similarity+flow STN @128, perceptual VGG16 loss, "
+            "Adam, EMA), synthetic latents + seeded random weights")
+
+
+def workload_config(args, dtype="f32"):
+    return {"workload": WORKLOAD + (" -- BASELINE config 2 (fp32)" if dtype == "f32" else
+                                    " -- BASELINE config 3 (bf16 activations, fp32 master weights / accumulation)"),
             "step_mode": "eager" if args.no_graph else "whole-step CUDA graph replay",
             "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "gen_size": 256, "flow_size": 128,
             "parallelism": "dp%d" % args.gpus, "activation_layout": "NHWC (channels-last) generator + STN trunk",
@@ -122,46 +129,46 @@ def cpu_step_rate(batch, steps=1, warmup=0):
 
 
 def run_reference(args):
+    """The reference algorithm on the host cores.  The line reports what THIS arm ran (CPU, eager, NCHW, a bounded per-step
+    batch), not the GPU arm's configuration; --steps / --warmup are honoured up to a wall-clock bound (each CPU step of
+    batch 2 takes 5-20 s), and the clamp is stated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
     cores = cpu_threads()
-    steps = max(1, min(args.steps, 2))  # bounded sample: each CPU step of B=2 takes ~10-20 s
-    warm = 1 if args.warmup > 0 else 0
+    max_steps = int(os.environ.get("GG_CPU_MAX_STEPS", "6"))
+    steps = max(1, min(args.steps, max_steps))
+    warm = max(0, min(args.warmup, 1))
     rate, sec = cpu_step_rate(args.cpu_batch, steps=steps, warmup=warm)
-    sample = "%d step(s) of per-step batch %d (of the %d-per-GPU workload), %d host threads" % (steps, args.cpu_batch, args.batch, cores)
+    sample = "%d step(s) of per-step batch %d (a bounded sample of the %d-per-GPU workload), %d host threads" % (
+        steps, args.cpu_batch, args.batch, cores)
+    cfg = {"workload": WORKLOAD + " -- BASELINE config 2 (fp32)", "step_mode": "eager, CPU (reference algorithm, oracle port)",
+           "per_step_batch": args.cpu_batch, "gen_size": 256, "flow_size": 128, "parallelism": "none (rank 0 host cores)",
+           "activation_layout": "NCHW", "host_threads": cores,
+           "steps_requested": args.steps, "warmup_requested": args.warmup,
+           "clamp": "steps <= %d, warmup <= 1: a CPU step takes seconds; the sample is bounded to keep the run within minutes" % max_steps}
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
+def measure(args, dtype, dev, rank, world, distributed, want_clocks):
+    """Build the trainer for `dtype`, warm up, probe the roofline kernel, capture the step, time `args.steps` steps twice
+    (device-resident latents; end to end with host latents) -> dict of raw measurements (max over ranks)."""
     import torch.distributed as dist
     from gangealing_b200 import _lib
     from gangealing_b200.op import styled_tail
     from gangealing_b200.training import TrainConfig, Trainer
-    from gangealing_b200.training import distributed as gdist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    distributed = world > 1
-    if distributed:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required for capturing NCCL work in CUDA graphs
-        gdist.setup_distributed("nccl")
-    torch.cuda.set_device(local_rank)
-    dev = "cuda:%d" % local_rank
-    rank = gdist.get_rank()
-    torch.backends.cudnn.benchmark = True
-
-    phase("process group ready (world %d)" % world)
-    cfg = TrainConfig(batch=args.batch)
+    cfg = TrainConfig(batch=args.batch, dtype=dtype, grad_compression=os.environ.get("GG_GRAD_COMPRESSION", "bf16" if dtype == "bf16" else "none"),
+                      bucket_cap_mb=int(os.environ.get("GG_BUCKET_MB", "25")))
     tr = Trainer(cfg, dev, distributed=distributed)
-    phase("trainer built")
+    phase("trainer built (%s)" % dtype)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -186,23 +193,15 @@ def run_ours(args):
     calls_per_step = (_lib.CALLS - calls0) // probe_steps
     timing, styled_tail.TIMING = styled_tail.TIMING, None
 
-    use_graph = not args.no_graph
-    if use_graph:
-        try:
-            tr.capture(warmup=2)
-            phase("step captured as a CUDA graph")
-            for _ in range(2):
-                tr.step()
-        except Exception as exc:  # keep the bench alive: fall back to eager steps and say so
-            if distributed:
-                raise
-            print("CUDA graph capture failed (%r); running eagerly" % (exc,), file=sys.stderr)
-            tr._graph = None
-            use_graph = False
+    if not args.no_graph:
+        tr.capture(warmup=2)   # a capture failure is an error: the bench never silently measures a different mode
+        phase("step captured as a CUDA graph")
+        for _ in range(2):
+            tr.step()
         sync_all()
 
     # ---- timed region 1: device-resident inputs (latents drawn on the device, like reference loss.py:24)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and want_clocks) else None
     if sampler:
         sampler.start()
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -219,7 +218,6 @@ def run_ours(args):
         torch.cuda.cudart().cudaProfilerStop()
     ms = st.elapsed_time(en)
     phase("timed region 1 done")
-    calls = calls_per_step * args.steps
     if sampler:
         sampler.stop_flag.set()
 
@@ -242,35 +240,83 @@ def run_ours(args):
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms2 = t.tolist()
+    return {"tr": tr, "cfg": cfg, "ms": ms, "ms2": ms2, "timing": timing, "calls": calls_per_step * args.steps,
+            "clocks": sampler.summary() if sampler else None, "losses": {k: float(v.detach()) for k, v in out.items()}}
+
+
+def roofline_of(m, args, dtype):
+    """Roofline of the dominant hand-written kernel: the fused blur+noise+bias+act tail at the 256^2 layer."""
+    timing = m["timing"]
+    if not timing:
+        return None
+    peak, peak_src = peaks()
+    biggest = max(t_[2] for t_ in timing)
+    sel = [t_ for t_ in timing if t_[2] == biggest]
+    durs = [a.elapsed_time(b) for a, b, _ in sel]
+    avg_ms = sum(durs) / len(durs)
+    achieved = biggest / (avg_ms * 1e-3) / 1e9
+    kname = "blur_nhwc_kernel<%s, MODE=1 (fused tail), SEP=1> (channels-last blur+noise+bias+lrelu tail, 256^2 layer)" % (
+        "float" if dtype == "f32" else "__nv_bfloat16")
+    # DRAM bytes per launch of this kernel from a committed `ncu --set full` capture (same shape, batch and dtype only)
+    traffic, traffic_src = None, None
+    for name in ("r02_nhwc_b32_traffic_%s.json" % dtype, "r01_nhwc_b32_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("per_gpu_batch") == args.batch and tj.get("dtype", "f32") == dtype:
+                for k, v in tj["kernels"].items():
+                    if k.startswith("blur_nhwc_kernel") and v.get("fused_tail", True):
+                        traffic = v.get("dram_bytes_per_launch")
+                        traffic_src = "ncu --set full capture committed as profiles/%s (not measured by this run)" % name
+                        break
+            if traffic is not None:
+                break
+    return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": biggest, "launches_timed": len(durs), "avg_launch_ms": avg_ms, "peak_source": peak_src}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from gangealing_b200.training import distributed as gdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required for capturing NCCL work in CUDA graphs
+        gdist.setup_distributed("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    rank = gdist.get_rank()
+    torch.backends.cudnn.benchmark = True
+    phase("process group ready (world %d)" % world)
+
+    m = measure(args, args.dtype, dev, rank, world, distributed, want_clocks=True)
+    images = args.batch * world * args.steps
+    extra = None
+    other = "bf16" if args.dtype == "f32" else None
+    if other and os.environ.get("GG_BENCH_EXTRA", "1") == "1" and not args.no_extra:
+        # BASELINE config 3 (bf16 activations) measured in the same run, same box, same steps: reported under `config3_bf16`
+        tr0 = m.pop("tr")
+        tr0.release_graph()
+        del tr0
+        torch.cuda.empty_cache()
+        m3 = measure(args, other, dev, rank, world, distributed, want_clocks=False)
+        extra = {"metric": METRIC, "dtype": "bf16", "value": images / (m3["ms"] / 1e3), "unit": UNIT, "ms_per_step": m3["ms"] / args.steps,
+                 "e2e": {"value": images / (m3["ms2"] / 1e3), "unit": UNIT, "ms_per_step": m3["ms2"] / args.steps},
+                 "config": workload_config(args, "bf16"), "roofline": roofline_of(m3, args, "bf16") if rank == 0 else None,
+                 "gpu_launches": m3["calls"], "losses": m3["losses"], "grad_allreduce": m3["cfg"].grad_compression}
+        m["tr"] = m3.pop("tr")
+    tr = m["tr"]
     if rank != 0:
         finish(distributed, tr)
         return
-
-    images = args.batch * world * args.steps
+    ms, ms2 = m["ms"], m["ms2"]
     value = images / (ms / 1e3)
     e2e = images / (ms2 / 1e3)
-    # roofline of the dominant hand-written kernel: the fused blur+noise+bias+act tail at the 256^2 layer
-    peak, peak_src = peaks()
-    roof = None
-    if timing:
-        biggest = max(t_[2] for t_ in timing)
-        sel = [t_ for t_ in timing if t_[2] == biggest]
-        durs = [a.elapsed_time(b) for a, b, _ in sel]
-        avg_ms = sum(durs) / len(durs)
-        achieved = biggest / (avg_ms * 1e-3) / 1e9
-        kname = ("blur_nhwc_kernel<FUSED=1,SEP=1> (channels-last blur+noise+bias+lrelu tail, 256^2 layer)" if cfg.channels_last
-                 else "fir4_band_kernel<float,*,FUSED> (blur+noise+bias+lrelu, 256^2 layer)")
-        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (same shape and batch only)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_nhwc_b32_traffic.json")
-        if cfg.channels_last and os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if tj.get("per_gpu_batch") == args.batch:
-                traffic = tj["kernels"].get("blur_nhwc_kernel<1, 1>", {}).get("dram_bytes_per_launch")
-        roof = {"bound": "hbm", "kernel": kname,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": biggest, "launches_timed": len(durs), "avg_launch_ms": avg_ms,
-                "peak_source": peak_src}
+    cfg = m["cfg"]
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -282,12 +328,13 @@ def run_ours(args):
             cpu = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": "failed: %r" % (exc,)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, args.dtype),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.batch * cfg.dim_latent * 4 * world,
                     "d2h_bytes_per_step": 12 * world, "ms_per_step": ms2 / args.steps},
-            "gpu_launches": calls, "roofline": roof, "cpu_baseline": cpu,
-            "clocks": sampler.summary() if sampler else None,
-            "losses": {k: float(v.detach()) for k, v in out.items()}}
+            "gpu_launches": m["calls"], "roofline": roofline_of(m, args, args.dtype), "cpu_baseline": cpu,
+            "clocks": m["clocks"], "losses": m["losses"]}
+    if extra is not None:
+        line["config3_bf16"] = extra
     print(json.dumps(line), flush=True)
     phase("result printed")
     finish(distributed, tr)

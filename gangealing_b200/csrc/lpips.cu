@@ -6,6 +6,7 @@
 // on five feature maps x two images every step; here ONE pass forward (reads both maps) and ONE pass backward
 // (reads both maps, writes both gradients):
 //     d[n] = 1/HW * sum_p sum_c w[c] * (a[n,p,c]/(|a[n,p,:]|+eps) - b[n,p,c]/(|b[n,p,:]|+eps))^2
+// Feature maps are stored fp32 or bf16 (`dtype`; BASELINE config 3 runs the VGG in bf16); arithmetic and the result are fp32.
 // A group of L = min(32, C/4) lanes owns one pixel: every lane keeps its channel quads of both maps in registers
 // (<= 8 independent 128-bit loads in flight), the per-pixel sums are butterfly reductions inside the group, and the
 // difference is formed from the normalised values themselves (no |a|^2 + |b|^2 - 2ab cancellation).
@@ -17,6 +18,18 @@ namespace {
 constexpr int kT = 256;
 constexpr int kMaxTrips = 8;     // C <= 4 * 32 * 8 = 1024
 
+// 4 consecutive channels of a feature map as fp32 (storage: fp32 -> one 16-byte access, bf16 -> one 8-byte access)
+__device__ __forceinline__ float4 ld4(const float* base, int64_t quad) { return __ldcs(reinterpret_cast<const float4*>(base) + quad); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* base, int64_t quad) {
+  const uint2 u = __ldcs(reinterpret_cast<const uint2*>(base) + quad);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ void st4(float* base, int64_t quad, const float4 v) { reinterpret_cast<float4*>(base)[quad] = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* base, int64_t quad, const float4 v) {
+  reinterpret_cast<uint2*>(base)[quad] = make_uint2(ChanVec<__nv_bfloat16>::pack2(v.x, v.y), ChanVec<__nv_bfloat16>::pack2(v.z, v.w));
+}
+
 template <int L>
 __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 #pragma unroll
@@ -25,10 +38,10 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 }
 
 // TRIPS channel quads per lane (compile time): registers, no local memory.
-template <int L, int TRIPS, bool BACKWARD>
+template <typename T, int L, int TRIPS, bool BACKWARD>
 __global__ void __launch_bounds__(kT)
-feature_distance_kernel(float* __restrict__ partial, float* __restrict__ g0, float* __restrict__ g1,
-                        const float* __restrict__ gout, const float* __restrict__ f0, const float* __restrict__ f1,
+feature_distance_kernel(float* __restrict__ partial, T* __restrict__ g0, T* __restrict__ g1,
+                        const float* __restrict__ gout, const T* __restrict__ f0, const T* __restrict__ f1,
                         const float* __restrict__ w, int c4, int64_t hw, int chunk, int chunks_per_sample, float eps,
                         float inv_hw) {
   __shared__ float red[kT / 32];
@@ -47,13 +60,11 @@ feature_distance_kernel(float* __restrict__ partial, float* __restrict__ g0, flo
   float acc = 0.f;
   for (int64_t p = p0 + grp; p < p1; p += GROUPS) {
     const int64_t base = (n * hw + p) * c4;
-    const float4* ap = reinterpret_cast<const float4*>(f0) + base;
-    const float4* bp = reinterpret_cast<const float4*>(f1) + base;
     float4 a[TRIPS], b[TRIPS];
 #pragma unroll
-    for (int t = 0; t < TRIPS; ++t) a[t] = __ldcs(ap + l + t * L);
+    for (int t = 0; t < TRIPS; ++t) a[t] = ld4(f0, base + l + t * L);
 #pragma unroll
-    for (int t = 0; t < TRIPS; ++t) b[t] = __ldcs(bp + l + t * L);
+    for (int t = 0; t < TRIPS; ++t) b[t] = ld4(f1, base + l + t * L);
     float saa = 0.f, sbb = 0.f;
 #pragma unroll
     for (int t = 0; t < TRIPS; ++t) {
@@ -91,20 +102,18 @@ feature_distance_kernel(float* __restrict__ partial, float* __restrict__ g0, flo
       const float ka = ra > 0.f ? pa * ia * ia / ra : 0.f;
       const float kb = rb > 0.f ? pb * ib * ib / rb : 0.f;
       const float gsa = ra > 0.f ? gs : 0.f, gsb = rb > 0.f ? gs : 0.f;
-      float4* g0p = reinterpret_cast<float4*>(g0) + base;
-      float4* g1p = reinterpret_cast<float4*>(g1) + base;
 #pragma unroll
       for (int t = 0; t < TRIPS; ++t) {
         float4 o;
         if (g0) {
           o.x = gsa * (tq[t].x * ia - a[t].x * ka); o.y = gsa * (tq[t].y * ia - a[t].y * ka);
           o.z = gsa * (tq[t].z * ia - a[t].z * ka); o.w = gsa * (tq[t].w * ia - a[t].w * ka);
-          g0p[l + t * L] = o;
+          st4(g0, base + l + t * L, o);
         }
         if (g1) {
           o.x = -gsb * (tq[t].x * ib - b[t].x * kb); o.y = -gsb * (tq[t].y * ib - b[t].y * kb);
           o.z = -gsb * (tq[t].z * ib - b[t].z * kb); o.w = -gsb * (tq[t].w * ib - b[t].w * kb);
-          g1p[l + t * L] = o;
+          st4(g1, base + l + t * L, o);
         }
       }
     }
@@ -140,8 +149,8 @@ int64_t distance_chunk(int64_t N, int64_t HW, int groups) {
   return (HW + k - 1) / k;
 }
 
-template <bool BACKWARD>
-int launch_distance(float* partial, float* g0, float* g1, const float* gout, const float* f0, const float* f1,
+template <typename T, bool BACKWARD>
+int launch_distance(float* partial, T* g0, T* g1, const float* gout, const T* f0, const T* f1,
                     const float* w, int64_t N, int C, int64_t HW, float eps, cudaStream_t st, int* k_out) {
   const int c4 = C / 4;
   const int L = c4 >= 32 ? 32 : c4;         // c4 is a power of two here when < 32 (checked by the caller)
@@ -153,7 +162,7 @@ int launch_distance(float* partial, float* g0, float* g1, const float* gout, con
   const unsigned grid = static_cast<unsigned>(N * K);
   const float inv_hw = 1.f / static_cast<float>(HW);
 #define GG_DIST(L_, T_)                                                                                          \
-  feature_distance_kernel<L_, T_, BACKWARD><<<grid, kT, 0, st>>>(partial, g0, g1, gout, f0, f1, w, c4, HW, chunk, K, \
+  feature_distance_kernel<T, L_, T_, BACKWARD><<<grid, kT, 0, st>>>(partial, g0, g1, gout, f0, f1, w, c4, HW, chunk, K, \
                                                                  eps, inv_hw)
   if (L == 32) {
     switch (trips) {
@@ -199,8 +208,9 @@ int64_t gg_feature_distance_workspace(int64_t N, int C, int64_t HW) {
   return N * ((HW + chunk - 1) / chunk) * static_cast<int64_t>(sizeof(float));
 }
 
-int gg_feature_distance_forward(float* out, void* workspace, const float* f0, const float* f1, const float* weight,
-                                int64_t N, int C, int64_t HW, float eps, void* stream) {
+int gg_feature_distance_forward(float* out, void* workspace, const void* f0, const void* f1, const float* weight,
+                                int dtype, int64_t N, int C, int64_t HW, float eps, void* stream) {
+  if (dtype != GG_F32 && dtype != GG_BF16) return fail(GG_ERR_UNSUPPORTED, "feature_distance: dtype %d not supported (fp32 or bf16)", dtype);
   int rc = check_distance("feature_distance", N, C, HW);
   if (rc != GG_OK) return rc;
   if (N == 0) return GG_OK;
@@ -213,7 +223,13 @@ int gg_feature_distance_forward(float* out, void* workspace, const float* f0, co
   }
   if (!f0 || !f1 || !workspace) return fail(GG_ERR_BAD_ARG, "feature_distance: null tensor");
   int K = 1;
-  rc = launch_distance<false>(static_cast<float*>(workspace), nullptr, nullptr, nullptr, f0, f1, weight, N, C, HW, eps, st, &K);
+  if (dtype == GG_F32)
+    rc = launch_distance<float, false>(static_cast<float*>(workspace), nullptr, nullptr, nullptr, static_cast<const float*>(f0),
+                                       static_cast<const float*>(f1), weight, N, C, HW, eps, st, &K);
+  else
+    rc = launch_distance<__nv_bfloat16, false>(static_cast<float*>(workspace), nullptr, nullptr, nullptr,
+                                               static_cast<const __nv_bfloat16*>(f0), static_cast<const __nv_bfloat16*>(f1),
+                                               weight, N, C, HW, eps, st, &K);
   if (rc != GG_OK) return rc;
   GG_CHECK_LAUNCH("feature_distance forward launch");
   distance_finish_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(out, static_cast<const float*>(workspace), N, K);
@@ -221,13 +237,20 @@ int gg_feature_distance_forward(float* out, void* workspace, const float* f0, co
   return GG_OK;
 }
 
-int gg_feature_distance_backward(float* g0, float* g1, const float* grad_out, const float* f0, const float* f1,
-                                 const float* weight, int64_t N, int C, int64_t HW, float eps, void* stream) {
+int gg_feature_distance_backward(void* g0, void* g1, const float* grad_out, const void* f0, const void* f1,
+                                 const float* weight, int dtype, int64_t N, int C, int64_t HW, float eps, void* stream) {
+  if (dtype != GG_F32 && dtype != GG_BF16) return fail(GG_ERR_UNSUPPORTED, "feature_distance backward: dtype %d not supported", dtype);
   int rc = check_distance("feature_distance backward", N, C, HW);
   if (rc != GG_OK) return rc;
   if (N * HW == 0 || C == 0) return GG_OK;
   if (!grad_out || !f0 || !f1 || (!g0 && !g1)) return fail(GG_ERR_BAD_ARG, "feature_distance backward: null tensor");
-  rc = launch_distance<true>(nullptr, g0, g1, grad_out, f0, f1, weight, N, C, HW, eps, static_cast<cudaStream_t>(stream), nullptr);
+  if (dtype == GG_F32)
+    rc = launch_distance<float, true>(nullptr, static_cast<float*>(g0), static_cast<float*>(g1), grad_out, static_cast<const float*>(f0),
+                                      static_cast<const float*>(f1), weight, N, C, HW, eps, static_cast<cudaStream_t>(stream), nullptr);
+  else
+    rc = launch_distance<__nv_bfloat16, true>(nullptr, static_cast<__nv_bfloat16*>(g0), static_cast<__nv_bfloat16*>(g1), grad_out,
+                                              static_cast<const __nv_bfloat16*>(f0), static_cast<const __nv_bfloat16*>(f1), weight, N,
+                                              C, HW, eps, static_cast<cudaStream_t>(stream), nullptr);
   if (rc != GG_OK) return rc;
   GG_CHECK_LAUNCH("feature_distance backward launch");
   return GG_OK;

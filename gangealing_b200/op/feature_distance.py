@@ -3,7 +3,7 @@ difference, optional per-channel weights, spatial mean.
 
 reference: models/losses/lpips.py:26-28 (`normalize_tensor`), :193-205 (difference, `lins` / channel sum), :226
 (`spatial_average`).  `feature_distance(f0, f1, weight=None)` returns (N, 1, 1, 1) like the reference's per-layer `res`.
-CUDA tensors only (like every op here: no CPU path in the product).  The fused kernels want channels-last fp32 feature
+CUDA tensors only (like every op here: no CPU path in the product).  The fused kernels want channels-last fp32 or bf16 feature
 maps (forward: one read of both maps; backward: one read + one write of both): other layouts / float dtypes are
 converted to that form first (one copy), anything the kernel cannot take (trainable `lins` weights, odd channel counts)
 raises -- there is no eager tensor-op route."""
@@ -20,8 +20,8 @@ def _channels_ok(c):
 
 
 def _as_kernel_input(f):
-    """channels-last fp32 view/copy of a (N, C, H, W) feature map (autograd-tracked conversion when one is needed)."""
-    if f.dtype != torch.float32:
+    """channels-last fp32 / bf16 view or copy of a (N, C, H, W) feature map (autograd-tracked conversion when needed)."""
+    if f.dtype not in (torch.float32, torch.bfloat16):
         f = f.float()
     if f.shape[1] > 1 and f.shape[2] * f.shape[3] > 1:
         f = f.contiguous(memory_format=torch.channels_last)
@@ -40,7 +40,7 @@ class _FeatureDistance(Function):
         out = torch.empty(n, dtype=torch.float32, device=f0.device)
         ws = torch.empty(max(1, lib.gg_feature_distance_workspace(n, c, h * w) // 4), dtype=torch.float32, device=f0.device)
         rc = lib.gg_feature_distance_forward(out.data_ptr(), ws.data_ptr(), f0.data_ptr(), f1.data_ptr(), _lib.ptr(wt),
-                                             n, c, h * w, eps, _lib.stream())
+                                             _lib.dtype_code(f0), n, c, h * w, eps, _lib.stream())
         _lib.check(rc, "gg_feature_distance_forward")
         ctx.save_for_backward(f0, f1, wt)
         ctx.eps = eps
@@ -57,7 +57,8 @@ class _FeatureDistance(Function):
         g1 = torch.empty_like(f1) if need1 else None
         if need0 or need1:
             rc = _lib.load().gg_feature_distance_backward(_lib.ptr(g0), _lib.ptr(g1), g.data_ptr(), f0.data_ptr(),
-                                                          f1.data_ptr(), _lib.ptr(wt), n, c, h * w, ctx.eps, _lib.stream())
+                                                          f1.data_ptr(), _lib.ptr(wt), _lib.dtype_code(f0), n, c, h * w, ctx.eps,
+                                                          _lib.stream())
             _lib.check(rc, "gg_feature_distance_backward")
         return g0, g1, None, None
 
@@ -74,4 +75,7 @@ def feature_distance(f0, f1, weight=None, eps=1e-10):
     if weight is not None and weight.requires_grad:
         raise RuntimeError("feature_distance: trainable `lins` weights are not supported (the reference trains with "
                            "frozen LPIPS weights, lpips.py:13-22)")
-    return _FeatureDistance.apply(_as_kernel_input(f0), _as_kernel_input(f1), weight, float(eps))
+    a, b = _as_kernel_input(f0), _as_kernel_input(f1)
+    if a.dtype != b.dtype:
+        a, b = a.float(), b.float()
+    return _FeatureDistance.apply(a, b, weight, float(eps))

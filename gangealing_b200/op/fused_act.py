@@ -76,14 +76,14 @@ def bias_act_backward_raw(grad_output, out, alpha, scale, want_bias_grad):
 
 class _FusedLeakyReLUGrad(Function):
     @staticmethod
-    def forward(ctx, grad_output, out, negative_slope, scale, want_bias_grad):
+    def forward(ctx, grad_output, out, negative_slope, scale, want_bias_grad, bias_dtype=None):
         gx, grad_bias = bias_act_backward_raw(grad_output, out, negative_slope, scale, want_bias_grad)
         ctx.save_for_backward(out)
         ctx.cfg = (negative_slope, scale)
         if grad_bias is None:
             grad_bias = gx.new_zeros(())  # placeholder, never used
-        else:
-            grad_bias = grad_bias.to(gx.dtype)
+        else:   # the reduction is fp32; it is handed back in the bias' own dtype (fp32 master parameters under bf16 activations)
+            grad_bias = grad_bias.to(bias_dtype if bias_dtype is not None else gx.dtype)
         return gx, grad_bias
 
     @staticmethod
@@ -92,7 +92,7 @@ class _FusedLeakyReLUGrad(Function):
         negative_slope, scale = ctx.cfg
         bias = gradgrad_bias if (gradgrad_bias is not None and gradgrad_bias.dim() == 1) else None
         gradgrad_out = fused_bias_act_raw(gradgrad_input, bias, out, 3, 1, negative_slope, scale)
-        return gradgrad_out, None, None, None, None
+        return gradgrad_out, None, None, None, None, None
 
 
 class FusedLeakyReLUFunction(Function):
@@ -109,15 +109,15 @@ class FusedLeakyReLUFunction(Function):
         else:
             out = fused_bias_act_raw(input, bias, None, 3, 0, negative_slope, scale)
         ctx.save_for_backward(out)
-        ctx.cfg = (negative_slope, scale)
+        ctx.cfg = (negative_slope, scale, bias.dtype if bias is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, grad_output):
         (out,) = ctx.saved_tensors
-        negative_slope, scale = ctx.cfg
+        negative_slope, scale, bias_dtype = ctx.cfg
         want_bias = ctx.needs_input_grad[1]
-        grad_input, grad_bias = _FusedLeakyReLUGrad.apply(grad_output, out, negative_slope, scale, want_bias)
+        grad_input, grad_bias = _FusedLeakyReLUGrad.apply(grad_output, out, negative_slope, scale, want_bias, bias_dtype)
         return grad_input, (grad_bias if want_bias else None), None, None
 
 

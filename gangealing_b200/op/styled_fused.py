@@ -142,8 +142,8 @@ def synthesis(generator, latent, noise, act_dtype=torch.float32):
             blur = None
             out_h, out_w = raw.shape[2], raw.shape[3]
         nz = noise[i]
-        if nz is None:   # same draw (shape, dtype, order) as NoiseInjection.forward, networks.py:293-296
-            nz = torch.empty(b, 1, out_h, out_w, device=raw.device, dtype=torch.float32).normal_()
+        if nz is None:   # same draw (shape, order) as NoiseInjection.forward, networks.py:293-296; always fp32
+            nz = type(layer.noise).sample(b, out_h, out_w, styles[0])
         demod = demod_coefficients(conv.weight, styles[i], conv.scale, conv.eps)
         s_next = styles[i + 1] if i + 1 < len(layers) else None
         wm = rgb_bias = skip = None

@@ -64,6 +64,8 @@ class SpatialTransformer(nn.Module):
         self.stn_in_size = flow_size
         self.is_flow = transform == "flow"
         self.channels_last = False        # run the conv trunk on NHWC activations (cuDNN's native layout; CUDA only)
+        self.act_dtype = torch.float32    # storage type of the trunk's activations (bf16: BASELINE config 3); the warp
+        #                                   heads, the sampling grid and the warped image always stay fp32
         channels = channel_table(channel_multiplier)
         convs = [ConvLayer(3, int(channels[flow_size]), 1, ops=ops)]
         log_size = int(math.log(flow_size, 2))
@@ -144,8 +146,10 @@ class SpatialTransformer(nn.Module):
         regression_input = self.input_downsample(input_img) if input_img.size(-1) > self.stn_in_size else input_img
         source = input_img if input_img_for_sampling is None else input_img_for_sampling
         if self.channels_last and regression_input.is_cuda:
-            regression_input = regression_input.contiguous(memory_format=torch.channels_last)
+            regression_input = regression_input.to(self.act_dtype).contiguous(memory_format=torch.channels_last)
         feat = self.final_conv(self.convs(regression_input))
+        if feat.dtype != torch.float32:   # grid coordinates need more than 8 bits of mantissa: heads run in fp32
+            feat = feat.float()
         if not self.is_flow:
             feat = self.final_linear(feat.reshape(feat.shape[0], -1))   # logical (C, H, W) order in either layout
         res = output_resolution if output_resolution is not None else self.stn_in_size

@@ -41,7 +41,9 @@ class _FirModule(nn.Module):
         self.ops = ops if ops is not None else cuda_ops()
 
     def forward(self, input):
-        return self.ops.upfirdn2d(input, self.kernel.type(input.dtype), up=self.up, down=self.down, pad=self.pad)
+        # the registered fp32 buffer itself is passed (the C ABI takes fp32 taps for every activation dtype): a per-call
+        # `.type(...)` copy would defeat the per-filter memo (separability test, flipped taps) and sync the host
+        return self.ops.upfirdn2d(input, self.kernel, up=self.up, down=self.down, pad=self.pad)
 
 
 class Upsample(_FirModule):
@@ -129,7 +131,9 @@ class FusedLeakyReLU(nn.Module):
         self.ops = ops if ops is not None else cuda_ops()
 
     def forward(self, input):
-        return self.ops.fused_leaky_relu(input, self.bias.type(input.dtype), self.negative_slope, self.scale)
+        # bf16 activations keep the fp32 master bias (the channels-last kernel takes fp32 per-channel constants)
+        bias = self.bias if input.dtype == torch.bfloat16 else self.bias.type(input.dtype)
+        return self.ops.fused_leaky_relu(input, bias, self.negative_slope, self.scale)
 
 
 class ModulatedConv2d(nn.Module):

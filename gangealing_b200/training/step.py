@@ -59,6 +59,11 @@ class TrainConfig:
     psi: float = 0.5
     seed: int = 0
     channels_last: bool = True        # generator + STN-trunk activations NHWC on CUDA (no cuDNN layout conversions)
+    dtype: str = "f32"                # "f32" (BASELINE config 2) or "bf16" (config 3): STORAGE type of the generator / STN
+    #                                   trunk / VGG activations; fp32 master weights, fp32 arithmetic in the fused kernels,
+    #                                   bf16 tensor-core convolutions, fp32 images / grids / losses / optimiser
+    grad_compression: str = "none"    # DDP gradient all-reduce: "none" (fp32) or "bf16" (compressed on the wire)
+    bucket_cap_mb: int = 25
 
 
 class Trainer:
@@ -76,13 +81,22 @@ class Trainer:
         self.stn = get_stn(list(cfg.transform), **kw).to(device)
         self.t_ema = get_stn(list(cfg.transform), **kw).to(device)
         self.t_ema.load_state_dict(self.stn.state_dict())
+        if cfg.dtype not in ("f32", "bf16"):
+            raise ValueError("TrainConfig.dtype must be 'f32' or 'bf16'")
+        act_dtype = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
+        if act_dtype != torch.float32 and not self.generator.channels_last:
+            raise RuntimeError("bf16 activations need the channels-last sm_100a path (CUDA device, channels_last=True)")
+        self.generator.act_dtype = act_dtype
         if self.generator.channels_last:
             for m in list(self.stn.modules()) + list(self.t_ema.modules()):
                 if hasattr(m, "channels_last") and hasattr(m, "stn_in_size"):
                     m.channels_last = True
+                    m.act_dtype = act_dtype
         self.ll = DirectionInterpolator(None, cfg.ndirs, cfg.inject, self.generator.n_latent, num_heads=cfg.num_heads,
                                         dim_latent=cfg.dim_latent).to(device)
         self.loss_fn = get_perceptual_loss(device, seed=cfg.seed + 1, ops=ops)
+        if act_dtype != torch.float32:
+            self.loss_fn.net.to(act_dtype)     # frozen VGG16: bf16 weights and feature maps, fp32 distance
         self.resize_fake2stn = (BilinearDownsample(cfg.gen_size // cfg.flow_size, 3, ops=ops).to(device)
                                 if cfg.gen_size > cfg.flow_size else nn.Sequential())
         requires_grad(self.generator, False)
@@ -96,8 +110,11 @@ class Trainer:
 
             def wrap():
                 self.stn = nn.parallel.DistributedDataParallel(self.stn, device_ids=ids, broadcast_buffers=False,
-                                                               gradient_as_bucket_view=True)
+                                                               gradient_as_bucket_view=True, bucket_cap_mb=cfg.bucket_cap_mb)
                 self.ll = nn.parallel.DistributedDataParallel(self.ll, device_ids=ids, broadcast_buffers=False)
+                if cfg.grad_compression == "bf16":   # halves the bytes of the one exchange step (172 MB of fp32 STN gradients)
+                    from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+                    self.stn.register_comm_hook(None, default_hooks.bf16_compress_hook)
             if on_gpu:  # built on a side stream so the wrapped step can later be captured into a CUDA graph
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())

@@ -305,14 +305,17 @@ GG_API int gg_to_rgb_nhwc_backward(float* gx, float* gwm, void* workspace, const
  * reference: models/losses/lpips.py:26-28 normalize_tensor, :193-195 squared difference, :197-205 per-channel `lins`
  * weights or plain channel sum, :226 spatial_average.
  *   out[n] = 1/HW * sum_p sum_c w[c] * (f0[n,p,c]/(|f0[n,p,:]|+eps) - f1[n,p,c]/(|f1[n,p,:]|+eps))^2
- * f0, f1: (N, HW, C) fp32 (NHWC); weight: (C) or NULL (= 1); C a power of two < 128, or a multiple of 128 up to 1024.
+ * f0, f1 (and g0, g1): (N, HW, C) NHWC stored as `dtype` = GG_F32 or GG_BF16 (fp32 arithmetic, fp32 out / grad_out);
+ * weight: (C) fp32 or NULL (= 1); C a power of two < 128, or a multiple of 128 up to 1024.
  * forward needs gg_feature_distance_workspace(N, C, HW) bytes (deterministic two-stage reduction).
  * backward: g0 / g1 (either may be NULL) = grad_out[n] * d out[n] / d f0 / d f1, one pass over both maps. */
 GG_API int64_t gg_feature_distance_workspace(int64_t N, int C, int64_t HW);
-GG_API int gg_feature_distance_forward(float* out, void* workspace, const float* f0, const float* f1,
-                                       const float* weight, int64_t N, int C, int64_t HW, float eps, void* stream);
-GG_API int gg_feature_distance_backward(float* g0, float* g1, const float* grad_out, const float* f0, const float* f1,
-                                        const float* weight, int64_t N, int C, int64_t HW, float eps, void* stream);
+GG_API int gg_feature_distance_forward(float* out, void* workspace, const void* f0, const void* f1,
+                                       const float* weight, int dtype, int64_t N, int C, int64_t HW, float eps,
+                                       void* stream);
+GG_API int gg_feature_distance_backward(void* g0, void* g1, const float* grad_out, const void* f0, const void* f1,
+                                        const float* weight, int dtype, int64_t N, int C, int64_t HW, float eps,
+                                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BilinearDownsample: reference models/spatial_transformers/antialiased_sampling.py:241-256 --

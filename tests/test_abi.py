@@ -53,10 +53,10 @@ def test_argument_validation_of_the_channels_last_and_loss_entry_points():
     dll = _lib.load()
     one = 1  # any non-null pointer value: validation must reject these calls before dereferencing anything
     # perceptual front end: C must be a power of two below 128 or a multiple of 128
-    assert dll.gg_feature_distance_forward(one, one, one, one, None, 2, 24, 16, 1e-10, None) == -2
+    assert dll.gg_feature_distance_forward(one, one, one, one, None, 0, 2, 24, 16, 1e-10, None) == -2
     assert b"feature_distance" in dll.gg_last_error()
-    assert dll.gg_feature_distance_forward(one, one, one, one, None, 2, 192, 16, 1e-10, None) == -2
-    assert dll.gg_feature_distance_backward(one, one, one, one, one, None, -1, 64, 16, 1e-10, None) == -1
+    assert dll.gg_feature_distance_forward(one, one, one, one, None, 0, 2, 192, 16, 1e-10, None) == -2
+    assert dll.gg_feature_distance_backward(one, one, one, one, one, None, 0, -1, 64, 16, 1e-10, None) == -1
     assert dll.gg_feature_distance_workspace(0, 64, 16) == 0
     # BilinearDownsample: stride range, reflection needs a plane larger than stride/2
     assert dll.gg_tent_downsample_forward(one, one, one, one, 1, 3, 8, 8, 0, None) == -2

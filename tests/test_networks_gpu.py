@@ -159,13 +159,158 @@ def test_config4_point_transfer_and_splat_vs_cpu_oracle():
         torch.backends.cudnn.allow_tf32 = old
 
 
-def test_cluster_config5_step_runs_on_gpu():
-    """BASELINE config 5 shape (K heads, flips, sample_from_full_res, reflection padding), shrunk: one optimisation step."""
+def _patched_noise(noise_by_size):
+    """Context: NoiseInjection.sample / the fused path's sampler return fixed tensors (per size, in call order)."""
+    import contextlib
+    import gangealing_b200.stylegan2.networks as nets
+
+    @contextlib.contextmanager
+    def ctx(dev):
+        it = {"i": 0}
+        orig = nets.NoiseInjection.sample
+
+        def sample(batch, h, w, like):     # both the layer-by-layer and the fused synthesis draw through this hook
+            cands = noise_by_size[(h, w)]
+            it["i"] += 1
+            return cands[it["i"] % len(cands)].to(dev)[:batch]
+        nets.NoiseInjection.sample = staticmethod(sample)
+        try:
+            yield
+        finally:
+            nets.NoiseInjection.sample = orig
+    return ctx
+
+
+def test_cluster_config5_step_matches_cpu_oracle():
+    """BASELINE config 5 (K heads, flips, sample_from_full_res, reflection padding; reference loss.py:78-92), shrunk: the
+    clustering loss on the GPU op set vs the same host code on the CPU oracle -- loss, EXACT cluster assignments, the
+    assigned heads' residual flow and the gradients."""
     from gangealing_b200.training import TrainConfig, Trainer
-    cfg = TrainConfig(gen_size=128, flow_size=64, dim_latent=64, n_mlp=2, batch=2, inject=3, num_heads=2, flips=True,
-                      ndirs=2, sample_from_full_res=True, padding_mode="reflection", gen_channel_multiplier=1,
-                      stn_channel_multiplier=0.25)
-    tr = Trainer(cfg, DEV)
-    out1 = tr.step()
-    out2 = tr.step()
-    assert all(torch.isfinite(v) for v in out2.values()) and float(out2["p"]) > 0
+    from gangealing_b200.training.losses import assign_fake_images_to_clusters, total_variation_loss
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        cfg = TrainConfig(gen_size=128, flow_size=64, dim_latent=64, n_mlp=2, batch=3, inject=3, num_heads=4, flips=True,
+                          ndirs=2, sample_from_full_res=True, padding_mode="reflection", gen_channel_multiplier=1,
+                          stn_channel_multiplier=0.25, tv_weight=10.0)
+        t_cpu = Trainer(cfg, "cpu", ops=opset.cpu_ops())
+        t_gpu = Trainer(cfg, DEV)
+        for a, b in ((t_cpu.generator, t_gpu.generator), (t_cpu.t_module, t_gpu.t_module), (t_cpu.ll_module, t_gpu.ll_module),
+                     (t_cpu.loss_fn, t_gpu.loss_fn)):
+            b.load_state_dict(a.state_dict())
+        g = torch.Generator().manual_seed(9)
+        with torch.no_grad():
+            for tr in (t_cpu, t_gpu):
+                for name, prm in list(tr.t_module.named_parameters()) + list(tr.ll_module.named_parameters()):
+                    if "warp_head" in name or "coefficients" in name:
+                        g.manual_seed(zlib.crc32(name.encode()) % 1000)
+                        prm.copy_((0.08 * torch.randn(prm.shape, generator=g)).to(prm.device))
+        sizes = sorted({(n.shape[2], n.shape[3]) for n in t_cpu.generator.make_noise(1)})
+        noise = {hw: [torch.randn(4 * cfg.batch, 1, hw[0], hw[1], generator=g) for _ in range(3)] for hw in sizes}
+        z = torch.randn(cfg.batch, cfg.dim_latent, generator=g)
+        res = []
+        for tr, dev in ((t_cpu, "cpu"), (t_gpu, DEV)):
+            with _patched_noise(noise)(dev):
+                assign, _, delta, _, _, collapsed = assign_fake_images_to_clusters(
+                    tr.generator, tr.stn, tr.ll, tr.loss_fn, tr.resize_fake2stn, tr.psi_t, cfg.batch, cfg.dim_latent,
+                    cfg.freeze_ll, cfg.num_heads, cfg.flips, dev, sample_from_full_res=True, z=z.to(dev), padding_mode="reflection")
+            with _patched_noise(noise)(dev):
+                ld = tr.losses(z.to(dev))
+                full = ld["p"] + cfg.tv_weight * ld["tv"]
+                grads = torch.autograd.grad(full, list(tr.t_module.parameters()) + [tr.ll_module.coefficients], allow_unused=True)
+            res.append((assign, collapsed, ld, grads))
+        (a_c, col_c, ld_c, g_c), (a_g, col_g, ld_g, g_g) = res
+        assert_close(col_g, col_c, rtol=2e-3, what="per-(image, head, flip) perceptual scores")
+        # assignments are integer work: exact wherever the two best scores are separated by more than the float tolerance
+        top2 = col_c.topk(2, dim=1, largest=False).values
+        decided = (top2[:, 1] - top2[:, 0]) > 5e-3 * top2[:, 1]
+        assert decided.any()
+        assert torch.equal(a_g.indices.cpu()[decided], a_c.indices[decided])
+        assert_close(ld_g["p"], ld_c["p"], rtol=2e-3, what="cluster perceptual loss")
+        assert_close(ld_g["tv"], ld_c["tv"], rtol=3e-3, what="tv of the assigned heads' flows")
+        pairs = [(a, b) for a, b in zip(g_c, g_g) if a is not None and b is not None]
+        assert len(pairs) > 20
+        assert_close(torch.cat([b.flatten().cpu() for _, b in pairs]), torch.cat([a.flatten() for a, _ in pairs]),
+                     rtol=3e-3, what="whole gradient")
+        out = t_gpu.step()
+        assert all(torch.isfinite(v) for v in out.values())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_config4_full_size_point_transfer_and_splat_vs_cpu_oracle():
+    """BASELINE config 4 at its real size: flow STN with supersize 512 and output_resolution 512, P = 25 233 points (disc of
+    radius 0.35*R rendered at R = 256, applications/propagate_to_images.py:44-78) -> uncongeal_points -> splat at sigma 0.3
+    and 1.3, one frame, GPU op set vs the CPU oracle."""
+    from gangealing_b200.splat2d import splat2d
+    from gangealing_b200.stn import get_stn
+    from oracle import splat as SP
+    kw = dict(flow_size=128, supersize=512, channel_multiplier=0.125, num_heads=1)
+    s_cpu = get_stn(["similarity", "flow"], ops=opset.cpu_ops(), **kw).eval()
+    opset.fill_parameters(s_cpu, 31, gain=0.2)
+    s_gpu = get_stn(["similarity", "flow"], **kw).eval()
+    s_gpu.load_state_dict(s_cpu.state_dict())
+    s_gpu.to(DEV)
+    g = torch.Generator().manual_seed(4)
+    img = (torch.rand(1, 3, 512, 512, generator=g) * 2 - 1)
+    R = 256
+    ys, xs = torch.meshgrid(torch.arange(float(R)), torch.arange(float(R)), indexing="ij")
+    disc = ((ys - R / 2) ** 2 + (xs - R / 2) ** 2) < (0.35 * R) ** 2
+    pts = torch.stack([xs[disc], ys[disc]], dim=1)[None] * (127.0 / (R - 1))     # congealed-frame (128 px) coordinates
+    assert pts.shape[1] == 25233
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            pc = s_cpu.uncongeal_points(img, pts, normalize_input_points=True, output_resolution=512, padding_mode="border")
+            pg = s_gpu.uncongeal_points(img.to(DEV), pts.to(DEV), normalize_input_points=True, output_resolution=512,
+                                        padding_mode="border")
+        assert_close(pg, pc, atol=5e-2, what="transferred points (pixels, 512^2 frame)")
+        colors = torch.randn(1, pts.shape[1], 3, generator=g)
+        for sigma in (0.3, 1.3):
+            expect = SP.splat_points_ref(img, pc, sigma, 0.75, colors)
+            got = SP.splat_points_ref(img.to(DEV), pc.to(DEV), sigma, 0.75, colors.to(DEV), splat_fn=splat2d)
+            assert_close(got, expect, rtol=1e-3, what="propagated image, sigma %.1f" % sigma)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_bf16_training_step_tracks_the_fp32_step():
+    """BASELINE config 3 (bf16 activations, fp32 master weights / accumulation) vs config 2 (fp32) on identical weights,
+    latents and noise: the loss within bf16 rounding noise, the gradient direction preserved."""
+    from gangealing_b200.training import TrainConfig, Trainer
+    kw = dict(gen_size=128, flow_size=64, dim_latent=64, n_mlp=2, batch=4, inject=3, tv_weight=100.0, gen_channel_multiplier=1,
+              stn_channel_multiplier=0.5)
+    t32 = Trainer(TrainConfig(dtype="f32", **kw), DEV)
+    t16 = Trainer(TrainConfig(dtype="bf16", **kw), DEV)
+    for a, b in ((t32.t_module, t16.t_module), (t32.ll_module, t16.ll_module)):
+        b.load_state_dict(a.state_dict())
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for tr in (t32, t16):
+            for name, prm in tr.t_module.named_parameters():
+                if "warp_head" in name:
+                    g.manual_seed(zlib.crc32(name.encode()) % 1000)
+                    prm.copy_((0.05 * torch.randn(prm.shape, generator=g)).to(prm.device))
+    z = torch.randn(4, 64, generator=g).to(DEV)
+    res = []
+    for tr in (t32, t16):
+        assert tr.generator.act_dtype == (torch.float32 if tr is t32 else torch.bfloat16)
+        torch.manual_seed(123)                        # identical device-side noise draws (fp32 noise in both modes)
+        ld = tr.losses(z)
+        full = ld["p"] + tr.cfg.tv_weight * ld["tv"]
+        grads = torch.autograd.grad(full, list(tr.t_module.parameters()) + [tr.ll_module.coefficients], allow_unused=True)
+        res.append((ld, torch.cat([x.flatten().float() for x in grads if x is not None])))
+    (l32, g32), (l16, g16) = res
+    assert abs(float(l16["p"]) - float(l32["p"])) <= 3e-2 * abs(float(l32["p"])), (float(l16["p"]), float(l32["p"]))
+    assert abs(float(l16["tv"]) - float(l32["tv"])) <= 5e-2 * abs(float(l32["tv"])) + 1e-8
+    cos = torch.nn.functional.cosine_similarity(g16, g32, dim=0).item()
+    assert cos > 0.98, cos
+    assert all(p.dtype == torch.float32 for p in t16.t_module.parameters())   # fp32 master weights
+    out = t16.step()
+    assert all(torch.isfinite(v) for v in out.values())
+    t16.capture(warmup=2)                             # the bf16 step is graph-capturable like the fp32 one
+    out = t16.step()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v) for v in out.values())
