@@ -161,6 +161,7 @@ def measure(args, dtype, dev, rank, world, distributed, want_clocks):
     (device-resident latents; end to end with host latents) -> dict of raw measurements (max over ranks)."""
     import torch.distributed as dist
     from gangealing_b200 import _lib
+    from gangealing_b200.op import nhwc as nhwc_ops
     from gangealing_b200.op import styled_tail
     from gangealing_b200.training import TrainConfig, Trainer
 
@@ -184,14 +185,15 @@ def measure(args, dtype, dev, rank, world, distributed, want_clocks):
     # ---- roofline probe: the dominant hand-written kernel (fused blur+noise+bias+lrelu tail) timed with CUDA
     #      events on its launching stream, inside real training steps of this workload (eager, so that the events
     #      bracket individual launches; a CUDA graph replay offers no per-kernel events)
-    styled_tail.TIMING = []
+    styled_tail.TIMING = []        # NCHW fused tail (not used by the channels-last pipeline)
+    nhwc_ops.TIMING = styled_tail.TIMING
     calls0 = _lib.CALLS
     probe_steps = 2
     for _ in range(probe_steps):
         tr.step()
     sync_all()
     calls_per_step = (_lib.CALLS - calls0) // probe_steps
-    timing, styled_tail.TIMING = styled_tail.TIMING, None
+    timing, styled_tail.TIMING, nhwc_ops.TIMING = styled_tail.TIMING, None, None
 
     if not args.no_graph:
         tr.capture(warmup=2)   # a capture failure is an error: the bench never silently measures a different mode

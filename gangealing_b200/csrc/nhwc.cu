@@ -462,6 +462,21 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
   };
   if (FUSED && noise) fetch_noise(0);
 
+  // MODE 2: the `mul` operand of the row an iteration completes is fetched one input row earlier (its HBM latency hides
+  // behind that row's shared-memory reads and arithmetic)
+  uint4 mcur[COLS], mnext[COLS];
+#pragma unroll
+  for (int j = 0; j < COLS; ++j) mcur[j] = mnext[j] = make_uint4(0u, 0u, 0u, 0u);
+  auto fetch_mul = [&](int ro_) {
+    if (ro_ >= 0 && ro_ < rows_out) {
+      const int64_t mo = (((static_cast<int64_t>(n) * p.out_h + oy0 + ro_) * p.out_w + xo) * p.c + c0) + cq * V;
+#pragma unroll
+      for (int j = 0; j < COLS; ++j)
+        if (okc[j]) mnext[j] = __ldg(reinterpret_cast<const uint4*>(mul + mo + static_cast<int64_t>(j) * p.c));
+    }
+  };
+  if (MODE == 2 && mul) { fetch_mul(-3 + 3); }   // row 0 is completed by input row 3
+
   // window: sep -> horizontal results hwin[4 rows][COLS][V]; else raw inputs rwin[4 rows][COLS+3][V]
   float hwin[SEP ? 4 : 1][COLS][V];
   float rwin[SEP ? 1 : 4][COLS + 3][V];
@@ -487,6 +502,11 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
     const T* st = tiles + stage * G::STAGE_ELEMS;
 #pragma unroll
     for (int rr = 0; rr < kRY; ++rr, ++r_in) {
+      if (MODE == 2 && mul) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) mcur[j] = mnext[j];
+        fetch_mul(r_in - 3 + 1);           // the row the NEXT iteration completes
+      }
       // COLS+3 input pixels (columns COLS*xg .. of the tile) x V channels of this thread
       const uint4* rowp = reinterpret_cast<const uint4*>(st + (rr * TW + COLS * xg) * CB) + cq;
       float q[COLS + 3][V];
@@ -546,7 +566,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
             if (okc[j]) {
               if (mul) {
                 float mf[V];
-                ChanVec<T>::unpack(__ldg(reinterpret_cast<const uint4*>(mul + ooff)), mf);
+                ChanVec<T>::unpack(mcur[j], mf);
 #pragma unroll
                 for (int k = 0; k < V; ++k) dacc[k] = fmaf(a4[k], mf[k], dacc[k]);
               }

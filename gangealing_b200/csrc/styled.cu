@@ -171,9 +171,10 @@ struct TailBwdParams {
 // Thread = (channel vector, pixel lane): a thread keeps its V channels for the whole chunk, so the per-channel sums live in
 // registers; they are combined across the CTA's pixel lanes through shared memory into one partial block per CTA.
 template <typename T>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2)
 styled_tail_bwd_nhwc_kernel(const TailBwdParams p) {
   constexpr int V = ChanVec<T>::V;
+  constexpr int U = (V == 4) ? 4 : 2;   // pixels in flight per thread: 3 x 16-byte loads each (register budget: 2 CTAs/SM)
   extern __shared__ float red[];                          // [pixel lanes][n_red][C]
   const int C = p.C, cv = C / V;
   const int64_t n = blockIdx.x / p.chunks_per_sample;
@@ -221,19 +222,19 @@ styled_tail_bwd_nhwc_kernel(const TailBwdParams p) {
       *reinterpret_cast<uint4*>(graw + off) = ChanVec<T>::pack(gt);
     };
     int64_t pp = p0 + pl;
-    for (; pp + 3 * lanes_p < p1; pp += 4 * lanes_p) {
-      uint4 gr[4], orw[4], rr[4];
-      float s[4][3];
-      int64_t off[4];
+    for (; pp + (U - 1) * lanes_p < p1; pp += U * lanes_p) {
+      uint4 gr[U], orw[U], rr[U];
+      float s[U][3];
+      int64_t off[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t pu = pp + u * lanes_p;
         off[u] = ((n * p.hw + pu) * cv + cq) * V;
         orw[u] = ldg_stream16(outp + off[u]);
         gr[u] = gxs ? ldg_stream16(gxs + off[u]) : zero;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t pu = pp + u * lanes_p;
         rr[u] = rawp ? ldg_stream16(rawp + off[u]) : zero;
         s[u][0] = g0 ? __ldg(g0 + pu) : 0.f;
@@ -241,7 +242,7 @@ styled_tail_bwd_nhwc_kernel(const TailBwdParams p) {
         s[u][2] = g0 ? __ldg(g0 + 2 * p.hw + pu) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) body(off[u], gr[u], orw[u], rr[u], s[u][0], s[u][1], s[u][2]);
+      for (int u = 0; u < U; ++u) body(off[u], gr[u], orw[u], rr[u], s[u][0], s[u][1], s[u][2]);
     }
     for (; pp < p1; pp += lanes_p) {
       const int64_t off = ((n * p.hw + pp) * cv + cq) * V;

@@ -10,6 +10,10 @@ from .. import _lib
 
 CL = torch.channels_last
 
+# bench.py sets this to a list to time every fused blur-tail launch (gg_blur_nhwc mode 1) with CUDA events on the launching
+# stream: entries are (start_event, end_event, algorithmic_bytes).  None (default): no instrumentation.
+TIMING = None
+
 
 def blur_multiple(t):
     """Channel multiple the TMA blur kernel wants: a CTA covers 8 threads x 16 bytes of channels."""
@@ -64,12 +68,22 @@ def blur(x, kernel, pad, mode=0, noise=None, noise_weight=None, bias=None, row_s
         dot = torch.empty((n, c), dtype=torch.float32, device=x.device)
         nbytes = lib.gg_blur_nhwc_workspace(code, n, c, in_h, in_w, kh, kw, pad[0], pad[1], pad[2], pad[3])
         ws = torch.empty(max(1, nbytes // 4), dtype=torch.float32, device=x.device)
+    timed = TIMING is not None and mode == 1
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = lib.gg_blur_nhwc(_lib.ptr(out), _lib.ptr(out2), x.data_ptr(), taps.data_ptr(), _lib.ptr(nz),
                           _lib.ptr(_f32(noise_weight, 1)), _lib.ptr(_f32(bias, c)), _lib.ptr(_f32(row_scale, n * c)),
                           _lib.ptr(_f32(scale2, n * c)), _lib.ptr(mul if dot is not None else None), _lib.ptr(dot), _lib.ptr(ws),
                           code, n, c, in_h, in_w, kh, kw, 1 if _lib.filter_is_separable(kernel) else 0, pad[0], pad[1],
                           pad[2], pad[3], mode, act, negative_slope, gain, _lib.stream())
     _lib.check(rc, "gg_blur_nhwc")
+    if timed:
+        ev1.record()
+        es = x.element_size()
+        writes = (out is not None) + (out2 is not None)
+        TIMING.append((ev0, ev1, es * n * c * (in_h * in_w + writes * out_h * out_w) + (4 * n * out_h * out_w if nz is not None else 0)
+                       + 4 * ((2 + (scale2 is not None)) * c + 1 + kh * kw)))
     return out, out2, dot
 
 

@@ -55,17 +55,8 @@ class _StyledTail(Function):
             if kernel is None:
                 out = K.noise_bias_act(x, noise, nw, b, rs, negative_slope, scale)
             else:
-                if TIMING is not None:
-                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    ev0.record()
                 out = K.blur(x, kernel, pad, mode=1, noise=noise, noise_weight=nw, bias=b, row_scale=rs,
-                             negative_slope=negative_slope, gain=scale)[0]
-                if TIMING is not None:
-                    ev1.record()
-                    es = x.element_size()
-                    kh, kw = kernel.shape
-                    TIMING.append((ev0, ev1, es * n * c * (in_h * in_w + out.shape[2] * out.shape[3])
-                                   + (4 * n * out.shape[2] * out.shape[3] if noise is not None else 0) + 4 * (c + 1 + kh * kw)))
+                             negative_slope=negative_slope, gain=scale)[0]      # timed through op.nhwc.TIMING
         elif kernel is None:
             out = torch.empty_like(x)
             nz = _noise_plane(noise, x, in_h, in_w)

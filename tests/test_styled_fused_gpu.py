@@ -42,6 +42,27 @@ def _inputs(n, c, h, w, blur, with_rgb, with_next, seed):
     return t
 
 
+def _dekink(t, blur, dtype, margin=2e-3):
+    """Leaky-ReLU is not differentiable at 0: a pre-activation within rounding of 0 takes a different slope in two correct
+    implementations, and the flip shows up at full size in the gradients.  Move `raw` a little wherever the oracle's
+    pre-activation is closer to 0 than `margin`, so every comparison below is taken away from the kink."""
+    k = so.make_kernel([1, 3, 3, 1]) * 4 if blur else None
+    for _ in range(8):
+        raw = t["raw"].to(dtype).float()
+        if blur:
+            pre = so.blur_noise_bias_act_ref(raw, k, (1, 1), t["noise"], t["nw"], t["bias"], negative_slope=1.0, scale=1.0, row_scale=t["demod"])
+        else:
+            pre = so.noise_bias_act_ref(raw * t["demod"][:, :, None, None], t["noise"], t["nw"], t["bias"], negative_slope=1.0, scale=1.0)
+        bad = (pre.abs() < margin).nonzero()
+        if bad.shape[0] == 0:
+            return t
+        off = 1 if blur else 0
+        for n, c, y, x in bad.tolist():
+            t["raw"][n, c, y + off, x + off] += 0.0625 * (1 + (y + x) % 3)
+        t["raw"] = t["raw"].to(dtype).float()
+    raise AssertionError("could not move the test inputs away from the activation kink")
+
+
 def _run_both(t, blur, dtype, slope=0.2):
     from gangealing_b200.op.styled_fused import fused_tail
     k = so.make_kernel([1, 3, 3, 1]) * 4 if blur else None
@@ -73,7 +94,7 @@ def _run_both(t, blur, dtype, slope=0.2):
     ((2, 256, 9, 7), False, False, True), ((2, 64, 17, 17), True, False, True), ((2, 128, 33, 41), True, False, True),
     ((1, 512, 9, 9), True, False, True)])
 def test_fused_tail_forward_and_all_gradients_vs_oracle(shape, blur, with_rgb, with_next, dtype):
-    t = _inputs(*shape, blur, with_rgb, with_next, seed=shape[1] + shape[2])
+    t = _dekink(_inputs(*shape, blur, with_rgb, with_next, seed=shape[1] + shape[2]), blur, dtype)
     (xs_o, rgb_o, go), (xs, rgb, gg) = _run_both(t, blur, dtype)
     lo = dtype == torch.bfloat16
     if xs_o is not None:
