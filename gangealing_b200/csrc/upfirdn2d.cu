@@ -49,10 +49,15 @@ __device__ __forceinline__ int floordiv(int a, int b) {  // b > 0
 }
 __device__ __forceinline__ int ceildiv_s(int a, int b) { return -floordiv(-a, b); }
 
-template <typename T, bool FUSED>
+// UPC / DNC: compile-time up / down factors (0 = runtime): the two resamplers of the hot path -- the to-RGB skip's x2
+// up-sampling and its backward (x2 decimation), networks.py:28-46 -- divide by a constant (shifts instead of 4 integer
+// divisions per output).
+template <typename T, bool FUSED, int UPC = 0, int DNC = 0>
 __global__ void __launch_bounds__(256)
 upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __restrict__ taps,
                          GenericParams p, Epilogue ep, int64_t total) {
+  if (UPC) { p.up_x = UPC; p.up_y = UPC; }
+  if (DNC) { p.down_x = DNC; p.down_y = DNC; }
   float nw = 0.f;
   if (FUSED) nw = ep.noise ? (ep.noise_weight ? __ldg(ep.noise_weight) : 1.f) : 0.f;
   // out[m, oy, ox] = sum_{ky,kx} U[oy*dy + ky, ox*dx + kx] * taps[kh-1-ky][kw-1-kx]
@@ -724,6 +729,12 @@ int launch_generic_t(void* out, const void* in, const float* filt, const Generic
   if (ep)
     upfirdn2d_generic_kernel<T, true><<<static_cast<unsigned>(grid), 256, 0, st>>>(
         static_cast<T*>(out), static_cast<const T*>(in), filt, gp, *ep, total);
+  else if (gp.up_x == 2 && gp.up_y == 2 && gp.down_x == 1 && gp.down_y == 1)
+    upfirdn2d_generic_kernel<T, false, 2, 1><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<T*>(out), static_cast<const T*>(in), filt, gp, Epilogue{}, total);
+  else if (gp.up_x == 1 && gp.up_y == 1 && gp.down_x == 2 && gp.down_y == 2)
+    upfirdn2d_generic_kernel<T, false, 1, 2><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<T*>(out), static_cast<const T*>(in), filt, gp, Epilogue{}, total);
   else
     upfirdn2d_generic_kernel<T, false><<<static_cast<unsigned>(grid), 256, 0, st>>>(
         static_cast<T*>(out), static_cast<const T*>(in), filt, gp, Epilogue{}, total);

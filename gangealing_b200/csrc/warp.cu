@@ -187,11 +187,13 @@ struct LevelInfo {
   bool pass;       // level gradient flows (inside both clamps)
 };
 
-__device__ __forceinline__ LevelInfo level_of_detail(const float* __restrict__ grid_n, int oy, int ox, int ho, int wo,
+// `grid_at(y, x) -> float2`: the sampling grid, read from a tensor or generated on the fly (fused compose)
+template <typename GridAt>
+__device__ __forceinline__ LevelInfo level_of_detail(GridAt grid_at, int oy, int ox, int ho, int wo,
                                                      int hs, int ws, float max_level, float min_level) {
   // antialiased_sampling.py:181-210 and :62-97
   auto coord = [&](int y, int x, float& cx, float& cy) {
-    const float2 g = *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(y) * wo + x) * 2);
+    const float2 g = grid_at(y, x);
     cx = (static_cast<float>(ws) - 1.f) * (g.x + 1.f) / 2.f;
     cy = (static_cast<float>(hs) - 1.f) * (g.y + 1.f) / 2.f;
   };
@@ -315,7 +317,8 @@ warp_fwd_kernel(T* __restrict__ out, float* __restrict__ levels_out, const T* __
     int l0 = 0, l1 = 0;
     float w = 0.f;
     if (MIP) {
-      const LevelInfo li = level_of_detail(grid_n, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
+      auto grid_at = [&](int y, int x) { return *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(y) * p.wo + x) * 2); };
+      const LevelInfo li = level_of_detail(grid_at, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
       l0 = li.l0; l1 = li.l1; w = li.w;
       if (levels_out) levels_out[idx] = li.level;
     }
@@ -330,6 +333,161 @@ warp_fwd_kernel(T* __restrict__ out, float* __restrict__ levels_out, const T* __
       }
       out[(plane * p.ho + oy) * static_cast<int64_t>(p.wo) + ox] = Cvt<T>::from_f(o);
     }
+  }
+}
+
+// ---------------------------------------------------------------- the STN's sampling in ONE pass
+// north_star: "the STN's antialiased bilinear grid_sample fused with flow-compose in one pass".  The sampling grid is never
+// read from memory: every output pixel GENERATES its coordinate (and those of its 4 neighbours, for the level of detail)
+// from the head's raw regression outputs --
+//   MODE 1 (SimilarityHead, warping_heads.py:120-136): F.affine_grid(theta, align_corners=False): g = theta . [x, y, 1],
+//           x = (2*ox + 1)/Wo - 1
+//   MODE 2 (FlowHead, warping_heads.py:180-193,239-244,268-277): RAFT convex up-sampling (softmax over 9 mask logits x the 3x3
+//           neighbourhood of s*low_flow) + identity + apply_affine(base_warp) + alpha lerp
+// and then runs the level-of-detail / trilinear sampling of warp_fwd_kernel.  The grid (and the residual flow the TV
+// regulariser needs) are WRITTEN as by-products (the callers return them), replacing affine_grid (a bmm + 3 elementwise
+// launches) or the separate flow_compose pass and the grid read-back.
+struct ComposeParams {
+  const float* theta;     // MODE 1: (N, 2, 3) sampling matrices.  MODE 2: base warp (N, 2, 3) or null
+  const float* low;       // MODE 2: (N, lh, lw, 2)
+  const float* mask;      // MODE 2: (N, 9*s*s, lh, lw)
+  const float* identity;  // MODE 2: (s*lh, s*lw, 2) identity sampling grid (the head's buffer)
+  const float* alpha;     // MODE 2: (N) or null
+  int lh, lw, s;
+  float* grid_out;        // (N, Ho, Wo, 2) or null
+  float* delta_out;       // MODE 2: (N, Ho, Wo, 2) or null
+};
+
+template <int MODE>
+__device__ __forceinline__ float2 compose_at(const ComposeParams& cp, const WarpParams& p, int64_t n, int y, int x,
+                                             float2* delta) {
+  if (MODE == 1) {
+    const float* M = cp.theta + n * 6;
+    const float bx = (2.f * static_cast<float>(x) + 1.f) / static_cast<float>(p.wo) - 1.f;
+    const float by = (2.f * static_cast<float>(y) + 1.f) / static_cast<float>(p.ho) - 1.f;
+    return make_float2(fmaf(M[0], bx, fmaf(M[1], by, M[2])), fmaf(M[3], bx, fmaf(M[4], by, M[5])));
+  } else {
+    const int h = y / cp.s, w = x / cp.s, sy = y - h * cp.s, sx = x - w * cp.s;
+    float lg[9], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      lg[k] = __ldg(cp.mask + ((((n * 9 + k) * cp.s + sy) * cp.s + sx) * cp.lh + h) * static_cast<int64_t>(cp.lw) + w);
+      mx = fmaxf(mx, lg[k]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { lg[k] = expf(lg[k] - mx); sum += lg[k]; }
+    const float inv = 1.f / sum;
+    float dx = 0.f, dy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
+      if (hh >= 0 && hh < cp.lh && ww >= 0 && ww < cp.lw) {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(cp.low + ((n * cp.lh + hh) * static_cast<int64_t>(cp.lw) + ww) * 2));
+        const float pk = lg[k] * inv;
+        dx = fmaf(pk, static_cast<float>(cp.s) * f.x, dx);
+        dy = fmaf(pk, static_cast<float>(cp.s) * f.y, dy);
+      }
+    }
+    if (delta) *delta = make_float2(dx, dy);
+    const float2 id = __ldg(reinterpret_cast<const float2*>(cp.identity + (static_cast<int64_t>(y) * p.wo + x) * 2));
+    float gx = id.x + dx, gy = id.y + dy;
+    if (cp.theta) {
+      const float* M = cp.theta + n * 6;
+      const float tx = M[0] * gx + M[1] * gy + M[2];
+      const float ty = M[3] * gx + M[4] * gy + M[5];
+      gx = tx; gy = ty;
+    }
+    if (cp.alpha) {
+      const float a = __ldg(cp.alpha + n);
+      gx = id.x + a * (gx - id.x);
+      gy = id.y + a * (gy - id.y);
+    }
+    return make_float2(gx, gy);
+  }
+}
+
+template <typename T, bool MIP, int MODE>
+__global__ void __launch_bounds__(256)
+warp_compose_fwd_kernel(T* __restrict__ out, float* __restrict__ levels_out, const T* __restrict__ src,
+                        const float* __restrict__ pyr, const ComposeParams cp, const __grid_constant__ WarpParams p,
+                        int64_t total) {
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % p.wo);
+    const int64_t t = idx / p.wo;
+    const int oy = static_cast<int>(t % p.ho);
+    const int64_t n = t / p.ho;
+    float2 delta = make_float2(0.f, 0.f);
+    const float2 g = compose_at<MODE>(cp, p, n, oy, ox, &delta);
+    if (cp.grid_out) *reinterpret_cast<float2*>(cp.grid_out + idx * 2) = g;
+    if (MODE == 2 && cp.delta_out) *reinterpret_cast<float2*>(cp.delta_out + idx * 2) = delta;
+    const SampleGeom s = sample_geom(g.x, g.y, p.hs, p.ws, p.pad_mode);
+    int l0 = 0, l1 = 0;
+    float w = 0.f;
+    if (MIP) {
+      auto grid_at = [&](int y, int x) { return (y == oy && x == ox) ? g : compose_at<MODE>(cp, p, n, y, x, nullptr); };
+      const LevelInfo li = level_of_detail(grid_at, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
+      l0 = li.l0; l1 = li.l1; w = li.w;
+      if (levels_out) levels_out[idx] = li.level;
+    }
+    for (int c = 0; c < p.c; ++c) {
+      const int64_t plane = n * p.c + c;
+      const T* src_plane = src + plane * p.hs * static_cast<int64_t>(p.ws);
+      const float o0 = sample_level<T, false>(src_plane, pyr, p, plane, l0, s, nullptr, nullptr);
+      float o = o0;
+      if (MIP && l1 != l0) {
+        const float o1 = sample_level<T, false>(src_plane, pyr, p, plane, l1, s, nullptr, nullptr);
+        o = o0 + w * (o1 - o0);
+      }
+      out[(plane * p.ho + oy) * static_cast<int64_t>(p.wo) + ox] = Cvt<T>::from_f(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- all pyramid levels in ONE launch
+// One CTA per image plane: level 1 is computed from the source (global / L2) into shared memory, every further level from
+// the previous one in shared memory; each level is also written to the pyramid buffer.  Used when levels 1..E of a plane
+// fit in shared memory (sources up to ~384^2); larger sources take one mip_down launch per level.
+template <typename T>
+__global__ void __launch_bounds__(512)
+mip_build_all_kernel(float* __restrict__ pyr, const T* __restrict__ src, const __grid_constant__ Pyramid py) {
+  extern __shared__ float lv[];               // levels 1..E back to back
+  const int64_t plane = blockIdx.x;
+  const float f[4] = {1.f, 3.f, 3.f, 1.f};
+  int sm_off = 0, prev_off = 0;
+  for (int i = 1; i <= py.extra; ++i) {
+    const int in_h = py.hp >> (i - 1), in_w = py.wp >> (i - 1);
+    const int oh = in_h >> 1, ow = in_w >> 1;
+    float* dst = lv + sm_off;
+    const float* prev = lv + prev_off;
+    float* gout = pyr + py.offset[i] + plane * oh * static_cast<int64_t>(ow);
+    for (int o = threadIdx.x; o < oh * ow; o += blockDim.x) {
+      const int y = o / ow, x = o - y * ow;
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        int yy = reflect_idx(2 * y + a - 1, in_h);
+        if (i == 1) yy = reflect_idx(yy - py.lp, py.hs);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          int xx = reflect_idx(2 * x + b - 1, in_w);
+          float v;
+          if (i == 1) {
+            xx = reflect_idx(xx - py.lp, py.ws);
+            v = Cvt<T>::to_f(src[(plane * py.hs + yy) * static_cast<int64_t>(py.ws) + xx]);
+          } else {
+            v = prev[yy * in_w + xx];
+          }
+          acc = fmaf(v, f[a] * f[b] * (1.f / 64.f), acc);
+        }
+      }
+      dst[o] = acc;
+      gout[o] = acc;
+    }
+    __syncthreads();
+    prev_off = sm_off;
+    sm_off += oh * ow;
   }
 }
 
@@ -383,7 +541,10 @@ warp_bwd_kernel(float* __restrict__ grad_src, float* __restrict__ grad_pyr, floa
     const SampleGeom s = sample_geom(g.x, g.y, p.hs, p.ws, p.pad_mode);
     LevelInfo li;
     li.l0 = li.l1 = 0; li.w = 0.f; li.pass = false;
-    if (MIP) li = level_of_detail(grid_n, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
+    if (MIP) {
+      auto grid_at = [&](int y, int x) { return *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(y) * p.wo + x) * 2); };
+      li = level_of_detail(grid_at, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
+    }
     float gix = 0.f, giy = 0.f, glevel = 0.f;
     for (int c = 0; c < p.c; ++c) {
       const int64_t plane = n * p.c + c;
@@ -452,6 +613,22 @@ inline int fill_params(WarpParams* wp, int64_t n, int c, int hs, int ws, int ho,
 
 template <typename T>
 int build_t(float* pyr, const void* src, const Pyramid& py, cudaStream_t st) {
+  int64_t sm_floats = 0;
+  for (int i = 1; i <= py.extra; ++i) sm_floats += static_cast<int64_t>(py.hp >> i) * (py.wp >> i);
+  if (py.extra >= 1 && sm_floats * 4 <= 200 * 1024 && py.planes <= 0x7fffffffLL) {
+    const size_t smem = static_cast<size_t>(sm_floats) * sizeof(float);
+    if (smem > 48 * 1024) {
+      static DeviceOnce configured;
+      if (configured.needed()) {
+        const cudaError_t e = cudaFuncSetAttribute(mip_build_all_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "mip_build_all smem opt-in");
+        configured.done();
+      }
+    }
+    mip_build_all_kernel<T><<<static_cast<unsigned>(py.planes), 512, smem, st>>>(pyr, static_cast<const T*>(src), py);
+    GG_CHECK_LAUNCH("mip_build_all launch");
+    return GG_OK;
+  }
   for (int i = 1; i <= py.extra; ++i) {
     const int in_h = py.hp >> (i - 1), in_w = py.wp >> (i - 1);
     const int64_t total = py.planes * (in_h >> 1) * static_cast<int64_t>(in_w >> 1);
@@ -548,6 +725,47 @@ int gg_mipmap_warp_forward(void* out, float* levels_out, const void* src, const 
   }
 #undef GG_FWD
   GG_CHECK_LAUNCH("warp_fwd launch");
+  return GG_OK;
+}
+
+int gg_stn_sample_forward(void* out, float* grid_out, float* delta_out, float* levels_out, const void* src,
+                          const float* pyramid, const float* theta, const float* low, const float* mask,
+                          const float* identity, const float* alpha, int mode, int dtype, int64_t N, int C, int hs, int ws,
+                          int ho, int wo, int lh, int lw, int s, int extra_levels, float max_level, float min_level,
+                          int padding_mode, void* stream) {
+  WarpParams wp;
+  int rc = fill_params(&wp, N, C, hs, ws, ho, wo, padding_mode, extra_levels, max_level, min_level);
+  if (rc != GG_OK) return rc;
+  if (mode != 1 && mode != 2) return fail(GG_ERR_BAD_ARG, "stn_sample: mode must be 1 (affine) or 2 (flow)");
+  const int64_t total = N * ho * static_cast<int64_t>(wo);
+  if (total == 0 || C == 0) return GG_OK;
+  if (!out || !src || (extra_levels > 0 && !pyramid)) return fail(GG_ERR_BAD_ARG, "stn_sample: null tensor");
+  if (mode == 1 && !theta) return fail(GG_ERR_BAD_ARG, "stn_sample: affine mode needs theta");
+  if (mode == 2) {
+    if (!low || !mask || !identity) return fail(GG_ERR_BAD_ARG, "stn_sample: flow mode needs low, mask and identity");
+    if (s < 1 || lh < 1 || lw < 1 || lh * s != ho || lw * s != wo)
+      return fail(GG_ERR_BAD_ARG, "stn_sample: the flow grid (%d x %d, x%d) must match the output size (%d x %d)", lh, lw, s, ho, wo);
+  }
+  ComposeParams cp;
+  cp.theta = theta; cp.low = low; cp.mask = mask; cp.identity = identity; cp.alpha = alpha;
+  cp.lh = lh; cp.lw = lw; cp.s = s; cp.grid_out = grid_out; cp.delta_out = delta_out;
+  auto st = static_cast<cudaStream_t>(stream);
+  const int gridsz = grid_for(total, 256);
+#define GG_SS(T_, MIP_, MODE_)                                                                                   \
+  warp_compose_fwd_kernel<T_, MIP_, MODE_><<<gridsz, 256, 0, st>>>(static_cast<T_*>(out), levels_out,            \
+                                                                 static_cast<const T_*>(src), pyramid, cp, wp, total)
+#define GG_SS_T(T_)                                                                       \
+  if (extra_levels > 0) { if (mode == 1) GG_SS(T_, true, 1); else GG_SS(T_, true, 2); }   \
+  else { if (mode == 1) GG_SS(T_, false, 1); else GG_SS(T_, false, 2); }
+  switch (dtype) {
+    case GG_F32: GG_SS_T(float); break;
+    case GG_F16: GG_SS_T(__half); break;
+    case GG_BF16: GG_SS_T(__nv_bfloat16); break;
+    default: return fail(GG_ERR_UNSUPPORTED, "stn_sample: dtype %d not supported", dtype);
+  }
+#undef GG_SS_T
+#undef GG_SS
+  GG_CHECK_LAUNCH("warp_compose_fwd launch");
   return GG_OK;
 }
 

@@ -34,6 +34,8 @@ def cuda_ops():
             grid_sample=_smp.grid_sample_bilinear,
             bilinear_downsample=_smp.bilinear_downsample,
             flow_compose=_flow.flow_compose,
+            stn_sample_affine=_smp.stn_sample_affine,     # one-pass sampling (grid generated inside the sampler)
+            stn_sample_flow=_smp.stn_sample_flow,
             splat2d=_splat2d,
             feature_distance=_fd.feature_distance,
         )

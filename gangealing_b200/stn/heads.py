@@ -102,8 +102,17 @@ class SimilarityHead(nn.Module):
         matrix = matrix.reshape(n * split, 2, 3)
         if split > 1:
             img = img.repeat_interleave(split, dim=0)
-        grid = F.affine_grid(matrix, img_size, align_corners=False)
-        out = self.warper(img, grid, padding_mode=padding_mode)
+        fused = getattr(self.ops, "stn_sample_affine", None)
+        if fused is not None and img.is_cuda:
+            # one pass: the affine sampling grid is generated inside the (antialiased) sampler and returned as a by-product
+            mip = isinstance(self.warper, MipmapWarp)
+            out, grid, levels = fused(img, matrix, (img_size[2], img_size[3]), self.warper.max_num_levels if mip else None,
+                                      0.0, padding_mode)
+            if mip:
+                self.warper._levels = levels
+        else:
+            grid = F.affine_grid(matrix, img_size, align_corners=False)
+            out = self.warper(img, grid, padding_mode=padding_mode)
         oob = check_if_warp_exceeds_image_boundaries(grid, image_bounds, img_size, split) if return_out_of_bounds else None
         if unfold:
             out = out.reshape(n, -1, img_size[1], img_size[2], img_size[3])
@@ -169,6 +178,27 @@ class FlowHead(nn.Module):
         mask = mask.reshape(n * split, -1, h, w)
         if base_warp is not None and base_warp.dim() == 4:
             base_warp = base_warp.reshape(-1, 2, 3)
+        fused = getattr(self.ops, "stn_sample_flow", None)
+        s_ = self.flow_downsample
+        one_pass = (fused is not None and img.is_cuda and not stop_grad
+                    and (output_resolution is None or output_resolution == s_ * h) and h == w)
+        if one_pass:
+            # ONE pass: convex up-sampling + identity + affine + alpha generated inside the antialiased sampler
+            if split > 1:
+                img = img.repeat_interleave(split, dim=0)
+            mip = isinstance(self.warper, MipmapWarp)
+            out, flow, delta_flow, levels = fused(img, low, mask, self.identity_flow, base_warp, alpha, s_,
+                                                  self.warper.max_num_levels if mip else None, 0.0, padding_mode)
+            if mip:
+                self.warper._levels = levels
+            img_size = torch.Size([img.size(0), img.size(1), flow.size(1), flow.size(2)])
+            oob = check_if_warp_exceeds_image_boundaries(flow, image_bounds, img_size, split) if return_out_of_bounds else None
+            if unfold:
+                k = self.num_heads
+                out = out.reshape(out.size(0) // k, k, out.size(1), out.size(2), out.size(3))
+                flow = flow.reshape(flow.size(0) // k, k, out.size(3), out.size(4), 2)
+                delta_flow = delta_flow.reshape(delta_flow.size(0) // k, k, s_ * h, s_ * w, 2)
+            return out, flow, delta_flow, oob
         delta_flow, flow = self._compose(low, mask, base_warp, alpha)
         if output_resolution is None:
             img_size = torch.Size([img.size(0) * split, flow.size(1), flow.size(2)])

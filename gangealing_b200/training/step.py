@@ -88,6 +88,11 @@ class Trainer:
             raise RuntimeError("bf16 activations need the channels-last sm_100a path (CUDA device, channels_last=True)")
         self.generator.act_dtype = act_dtype
         if self.generator.channels_last:
+            # 4-D STN parameters are STORED channels-last (KRSC): cuDNN's NHWC kernels take them as they are (no per-call
+            # weight re-layout copies), weight gradients come back in the same layout, and DDP's bucket views -- created
+            # from the parameters' strides -- match the gradients (round 1's "grad strides differ from bucket view" copies)
+            self.stn.to(memory_format=torch.channels_last)
+            self.t_ema.to(memory_format=torch.channels_last)
             for m in list(self.stn.modules()) + list(self.t_ema.modules()):
                 if hasattr(m, "channels_last") and hasattr(m, "stn_in_size"):
                     m.channels_last = True

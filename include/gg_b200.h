@@ -207,6 +207,25 @@ GG_API int gg_splat2d_forward(float* out, void* workspace, const float* input, c
                               int W, int soft_normalize, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The STN's sampling in ONE pass (north_star: "antialiased bilinear grid_sample fused with flow-compose in one pass").
+ * The sampling grid is generated per output pixel from the head's raw outputs instead of being read from memory:
+ *   mode 1  SimilarityHead (reference warping_heads.py:120-136): grid = F.affine_grid(theta (N, 2, 3), align_corners=False)
+ *   mode 2  FlowHead (warping_heads.py:180-193 upsample_flow, :239-244, :268-277 apply_affine): low (N, lh, lw, 2),
+ *           mask (N, 9*s*s, lh, lw), identity (s*lh, s*lw, 2), optional base warp `theta` (N, 2, 3) and alpha (N);
+ *           ho == s*lh, wo == s*lw
+ * then the level-of-detail selection + trilinear sample of gg_mipmap_warp_forward (antialiased_sampling.py:35-238) on
+ * `src` (N, C, hs, ws) and its `pyramid` (gg_mipmap_build; extra_levels == 0: plain bilinear sampling).
+ * Outputs: out (N, C, ho, wo); grid_out (N, ho, wo, 2) and delta_out (mode 2: the residual flow of the TV regulariser,
+ * reference models/losses/loss.py:4-12) are written as by-products (NULL: skipped); levels_out (N, ho, wo) or NULL.
+ * The backward pass is gg_mipmap_warp_backward on grid_out (+ gg_flow_compose_backward for mode 2).
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int gg_stn_sample_forward(void* out, float* grid_out, float* delta_out, float* levels_out, const void* src,
+                                 const float* pyramid, const float* theta, const float* low, const float* mask,
+                                 const float* identity, const float* alpha, int mode, int dtype, int64_t N, int C,
+                                 int hs, int ws, int ho, int wo, int lh, int lw, int s, int extra_levels,
+                                 float max_level, float min_level, int padding_mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Modulated-convolution weight path -- replaces the tensor-op chain of ModulatedConv2d.forward
  *   reference: models/stylegan2/networks.py:233-253 (modulate, demodulate), :255-262 (layout for the up-conv)
  *   weight (O, I, kk) fp32 [kk = k*k]; style (B, I) fp32 (output of the modulation EqualLinear).

@@ -15,9 +15,9 @@ for sm_100a ("the kernel bar").  No reference source is c
                                     like the .so files, no source text enters the repo) so that the UNMODIFIED
                                     reference Generator / get_stn / gangealing_loss can execute on the GPU box above
                                     gangealing_b200.compat (tests/test_reference_dropin_gpu.py: the "drops in
-                                    unchanged" claim of SURVEY.md 8(b)).  models/stylegan2/op and
-                                    models/spatial_transformers/antialiased_sampling.py are NOT compiled: those are
-                                    the kernel boundary the shim replaces.
+                                    unchanged" claim of SURVEY.md 8(b)).  models/stylegan2/op is NOT compiled (it is
+                                    the kernel boundary and JIT-builds CUDA at import); antialiased_sampling.py is
+                                    compiled only so that tools/opbench.py --stn can time the reference's MipmapWarp.
 """
 import os
 import shutil
@@ -62,7 +62,10 @@ def build(verbose=False):
 
 
 REFPY = os.path.join(OUT, "refpy")
-_REFPY_SKIP = (os.path.join("models", "stylegan2", "op"), os.path.join("models", "spatial_transformers", "antialiased_sampling.py"))
+# models/stylegan2/op JIT-builds CUDA at import and IS the kernel boundary; antialiased_sampling.py is the boundary too (the
+# shim registers this repo's module under its name first, so the compiled file is never imported by the drop-in tests) but
+# it is compiled so that tools/opbench.py --stn can TIME the reference's own MipmapWarp on the GPU next to the fused sampler
+_REFPY_SKIP = (os.path.join("models", "stylegan2", "op"),)
 _REFPY_UTILS = ("__init__.py", "distributed.py", "download.py", "annealing.py")
 
 

