@@ -39,6 +39,7 @@ SIGNATURES = {
     "gg_stn_sample_forward": (_I, [_P] * 11 + [_I, _I, _L] + [_I] * 9 + [_F, _F, _I, _P]),
     "gg_modconv_wsq": (_I, [_P, _P, _I, _I, _I, _P]),
     "gg_modconv_demod": (_I, [_P, _P, _P, _F, _F, _I, _I, _I, _P]),
+    "gg_modconv_demod_batched": (_I, [_I, _P, _P, _P, _P, _P, _P, _F, _I, _P]),
     "gg_modconv_modulate": (_I, [_P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P]),
     "gg_noise_bias_act_nhwc": (_I, [_P] * 6 + [_I, _F, _F, _L, _I, _L, _P]),
     "gg_nhwc_rowwise_workspace": (_L, [_L, _I, _L]),

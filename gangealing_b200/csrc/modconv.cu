@@ -102,10 +102,30 @@ __device__ __forceinline__ void st_tile_chunk(float* tile, int r, int c, float4 
 
 // NA = swizzle atoms (32-float k-blocks) staged per pipeline step: 2 when the B tiles are small enough, so that
 // 16 independent 16-byte loads per thread are in flight while the previous step's MMAs run.
+// One launch serves a BATCH of layers (the generator's 13 modulated convolutions are known up front: their demodulation
+// coefficients are independent small GEMMs, 4 CTAs each -- one 27 us launch per layer was pure latency): a CTA looks up
+// its layer by block index; every layer shares the batch size B.
+constexpr int kMaxDemodLayers = 32;
+struct DemodBatch {
+  const float* wsq[kMaxDemodLayers];
+  const float* style[kMaxDemodLayers];
+  float* out[kMaxDemodLayers];
+  float scale2[kMaxDemodLayers];
+  int O[kMaxDemodLayers], I[kMaxDemodLayers];
+  int first_block[kMaxDemodLayers + 1];
+  int layers;
+};
+
 template <int NA>
 __global__ void __launch_bounds__(kDemodThreads)
-demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, const float* __restrict__ style,
-                  float scale2, float eps, int B, int O, int I, int n_pad, int tmem_cols) {
+demod_umma_kernel(const __grid_constant__ DemodBatch batch, float eps, int B, int n_pad, int tmem_cols) {
+  int layer = 0;
+  while (layer + 1 < batch.layers && static_cast<int>(blockIdx.x) >= batch.first_block[layer + 1]) ++layer;
+  float* __restrict__ demod = batch.out[layer];
+  const float* __restrict__ wsq = batch.wsq[layer];
+  const float* __restrict__ style = batch.style[layer];
+  const float scale2 = batch.scale2[layer];
+  const int O = batch.O[layer], I = batch.I[layer];
   extern __shared__ __align__(1024) unsigned char smem[];
   // per atom: A_hi, A_lo (128 x 32 fp32 = 16 KB each), B_hi, B_lo (n_pad x 32 fp32 each)
   unsigned char* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // SWIZZLE_128B tiles: 1024-byte aligned
@@ -120,7 +140,7 @@ demod_umma_kernel(float* __restrict__ demod, const float* __restrict__ wsq, cons
   __shared__ int failed;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int o0 = blockIdx.x * 128;
+  const int o0 = (static_cast<int>(blockIdx.x) - batch.first_block[layer]) * 128;
 
   if (tid == 0) {
     mbar_init(&mma_bar, 1);
@@ -308,16 +328,11 @@ int gg_modconv_wsq(float* wsq, const float* weight, int O, int I, int kk, void* 
   return GG_OK;
 }
 
-int gg_modconv_demod(float* demod, const float* wsq, const float* style, float scale, float eps, int B, int O, int I,
-                     void* stream) {
-  if (B < 0 || O < 0 || I < 0) return fail(GG_ERR_BAD_ARG, "modconv_demod: bad shape");
-  if (B == 0 || O == 0) return GG_OK;
-  if (!demod || !wsq || !style) return fail(GG_ERR_BAD_ARG, "modconv_demod: null tensor");
-  if (B > 256) return fail(GG_ERR_UNSUPPORTED, "modconv_demod: batch %d > 256 (split the call)", B);
+static int launch_demod(const DemodBatch& batch, int blocks, int min_i, float eps, int B, cudaStream_t st) {
   const int n_pad = (B + 15) / 16 * 16;
   int tmem_cols = 32;
   while (tmem_cols < n_pad) tmem_cols <<= 1;
-  const int na = (n_pad <= 32 && I >= 4 * kBlockK) ? 4 : ((n_pad <= 64 && I > kBlockK) ? 2 : 1);
+  const int na = (n_pad <= 32 && min_i >= 4 * kBlockK) ? 4 : ((n_pad <= 64 && min_i > kBlockK) ? 2 : 1);
   const size_t smem = static_cast<size_t>(na) * (2 * 128 + 2 * n_pad) * kBlockK * sizeof(float) + 1024;
   static DeviceOnce configured;
   if (configured.needed()) {
@@ -329,18 +344,46 @@ int gg_modconv_demod(float* demod, const float* wsq, const float* style, float s
     if (e != cudaSuccess) return cuda_fail(e, "modconv_demod smem opt-in");
     configured.done();
   }
-  auto st = static_cast<cudaStream_t>(stream);
-  if (na == 4)
-    demod_umma_kernel<4><<<(O + 127) / 128, kDemodThreads, smem, st>>>(demod, wsq, style, scale * scale, eps, B, O, I,
-                                                                      n_pad, tmem_cols);
-  else if (na == 2)
-    demod_umma_kernel<2><<<(O + 127) / 128, kDemodThreads, smem, st>>>(demod, wsq, style, scale * scale, eps, B, O, I,
-                                                                      n_pad, tmem_cols);
-  else
-    demod_umma_kernel<1><<<(O + 127) / 128, kDemodThreads, smem, st>>>(demod, wsq, style, scale * scale, eps, B, O, I,
-                                                                      n_pad, tmem_cols);
+  if (na == 4) demod_umma_kernel<4><<<blocks, kDemodThreads, smem, st>>>(batch, eps, B, n_pad, tmem_cols);
+  else if (na == 2) demod_umma_kernel<2><<<blocks, kDemodThreads, smem, st>>>(batch, eps, B, n_pad, tmem_cols);
+  else demod_umma_kernel<1><<<blocks, kDemodThreads, smem, st>>>(batch, eps, B, n_pad, tmem_cols);
   GG_CHECK_LAUNCH("demod_umma launch");
   return GG_OK;
+}
+
+int gg_modconv_demod(float* demod, const float* wsq, const float* style, float scale, float eps, int B, int O, int I,
+                     void* stream) {
+  if (B < 0 || O < 0 || I < 0) return fail(GG_ERR_BAD_ARG, "modconv_demod: bad shape");
+  if (B == 0 || O == 0) return GG_OK;
+  if (!demod || !wsq || !style) return fail(GG_ERR_BAD_ARG, "modconv_demod: null tensor");
+  if (B > 256) return fail(GG_ERR_UNSUPPORTED, "modconv_demod: batch %d > 256 (split the call)", B);
+  DemodBatch batch;
+  batch.layers = 1;
+  batch.wsq[0] = wsq; batch.style[0] = style; batch.out[0] = demod; batch.scale2[0] = scale * scale;
+  batch.O[0] = O; batch.I[0] = I; batch.first_block[0] = 0; batch.first_block[1] = (O + 127) / 128;
+  return launch_demod(batch, (O + 127) / 128, I, eps, B, static_cast<cudaStream_t>(stream));
+}
+
+int gg_modconv_demod_batched(int layers, float* const* demod, const float* const* wsq, const float* const* style,
+                             const float* scale, const int* O, const int* I, float eps, int B, void* stream) {
+  if (layers < 0 || B < 0) return fail(GG_ERR_BAD_ARG, "modconv_demod_batched: bad shape");
+  if (layers == 0 || B == 0) return GG_OK;
+  if (layers > kMaxDemodLayers) return fail(GG_ERR_UNSUPPORTED, "modconv_demod_batched: more than %d layers", kMaxDemodLayers);
+  if (!demod || !wsq || !style || !scale || !O || !I) return fail(GG_ERR_BAD_ARG, "modconv_demod_batched: null table");
+  if (B > 256) return fail(GG_ERR_UNSUPPORTED, "modconv_demod_batched: batch %d > 256 (split the call)", B);
+  DemodBatch batch;
+  batch.layers = layers;
+  int blocks = 0, min_i = 1 << 30;
+  for (int l = 0; l < layers; ++l) {
+    if (O[l] < 1 || I[l] < 1) return fail(GG_ERR_BAD_ARG, "modconv_demod_batched: layer %d has an empty shape", l);
+    if (!demod[l] || !wsq[l] || !style[l]) return fail(GG_ERR_BAD_ARG, "modconv_demod_batched: layer %d has a null tensor", l);
+    batch.wsq[l] = wsq[l]; batch.style[l] = style[l]; batch.out[l] = demod[l]; batch.scale2[l] = scale[l] * scale[l];
+    batch.O[l] = O[l]; batch.I[l] = I[l]; batch.first_block[l] = blocks;
+    blocks += (O[l] + 127) / 128;
+    if (I[l] < min_i) min_i = I[l];
+  }
+  batch.first_block[layers] = blocks;
+  return launch_demod(batch, blocks, min_i, eps, B, static_cast<cudaStream_t>(stream));
 }
 
 int gg_modconv_modulate(float* out, const float* weight, const float* style, const float* demod, float scale, int B,

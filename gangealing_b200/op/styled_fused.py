@@ -21,8 +21,8 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from .. import _lib
-from . import conv2d_gradfix, nhwc
-from .modconv import channel_scale, demod_coefficients, shared_conv_weight
+from . import conv2d_gradfix, nhwc, style_path
+from .modconv import channel_scale, shared_conv_weight
 from .upfirdn2d import grad_pad, upfirdn2d
 
 CL = torch.channels_last
@@ -125,7 +125,11 @@ def synthesis(generator, latent, noise, act_dtype=torch.float32):
     layers = [generator.conv1] + list(generator.convs)
     rgbs = [generator.to_rgb1] + list(generator.to_rgbs)
     b = latent.shape[0]
-    styles = [layer.conv.modulation(latent[:, i]) for i, layer in enumerate(layers)]
+    # the whole style path up front, batched over layers (op/style_path.py): 3 GEMMs + 1 tcgen05 launch instead of 33 chains
+    styles, rgb_styles = style_path.all_styles(generator, latent, layers, rgbs, list(range(len(layers))),
+                                               [2 * r + 1 for r in range(len(rgbs))])
+    demods = style_path.all_demod([layer.conv.weight for layer in layers], styles, [layer.conv.scale for layer in layers],
+                                  layers[0].conv.eps)
     x0 = generator.input(latent).to(act_dtype).contiguous(memory_format=CL)
     xs = channel_scale(x0, styles[0])
     rgb = None
@@ -144,13 +148,13 @@ def synthesis(generator, latent, noise, act_dtype=torch.float32):
         nz = noise[i]
         if nz is None:   # same draw (shape, order) as NoiseInjection.forward, networks.py:293-296; always fp32
             nz = type(layer.noise).sample(b, out_h, out_w, styles[0])
-        demod = demod_coefficients(conv.weight, styles[i], conv.scale, conv.eps)
+        demod = demods[i]
         s_next = styles[i + 1] if i + 1 < len(layers) else None
         wm = rgb_bias = skip = None
         if not conv.upsample:          # conv1 and the second StyledConv of every resolution feed a ToRGB
             to_rgb = rgbs[i // 2]
             rconv = to_rgb.conv
-            s_rgb = rconv.modulation(latent[:, i + 1])
+            s_rgb = rgb_styles[i // 2]
             wm = (rconv.scale * rconv.weight[0, :, :, 0, 0]).unsqueeze(0) * s_rgb.unsqueeze(1)      # (B, 3, C)
             rgb_bias = to_rgb.bias
             if rgb is not None:

@@ -239,4 +239,6 @@ class Trainer:
         if not cfg.freeze_ll:
             self.ll_optim.step()
         accumulate(self.t_ema, self.t_module, self.accum)
-        return gdist.reduce_loss_dict(loss_dict)
+        # detached: a caller that keeps the returned dict must not keep the iteration's autograd graph (and its
+        # AccumulateGrad nodes, which are pinned to the stream they were created on) alive
+        return gdist.reduce_loss_dict({k: v.detach() for k, v in loss_dict.items()})

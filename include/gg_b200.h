@@ -240,6 +240,10 @@ GG_API int gg_stn_sample_forward(void* out, float* grid_out, float* delta_out, f
 GG_API int gg_modconv_wsq(float* wsq, const float* weight, int O, int I, int kk, void* stream);
 GG_API int gg_modconv_demod(float* demod, const float* wsq, const float* style, float scale, float eps, int B,
                             int O, int I, void* stream);
+/* all layers of a generator in ONE launch: tables (host arrays of `layers` entries) of per-layer demod (B, O[l]) outputs,
+ * wsq (O[l], I[l]), style (B, I[l]), scale, O, I; every layer shares the batch size B <= 256; layers <= 32. */
+GG_API int gg_modconv_demod_batched(int layers, float* const* demod, const float* const* wsq, const float* const* style,
+                                    const float* scale, const int* O, const int* I, float eps, int B, void* stream);
 GG_API int gg_modconv_modulate(float* out, const float* weight, const float* style, const float* demod,
                                float scale, int B, int O, int I, int kk, int transposed, void* stream);
 
