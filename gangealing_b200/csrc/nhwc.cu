@@ -498,6 +498,20 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
 #pragma unroll
       for (int j = 0; j < COLS; ++j) nzc[rr][j] = nzn[rr][j];
     if (FUSED && noise && it + 1 < n_stage_iters) fetch_noise(it + 1);
+    if (MODE == 2 && mul && it + 1 < n_stage_iters) {
+      // pull the `mul` rows the NEXT stage completes into L2 now (no registers held): the one-row-ahead register fetch
+      // below then only has to cover an L2 hit
+#pragma unroll
+      for (int rr = 0; rr < kRY; ++rr) {
+        const int ro = (it + 1) * kRY + rr - 3;
+        if (ro >= 0 && ro < rows_out) {
+          const T* mp = mul + (((static_cast<int64_t>(n) * p.out_h + oy0 + ro) * p.out_w + xo) * p.c + c0) + cq * V;
+#pragma unroll
+          for (int j = 0; j < COLS; ++j)
+            if (okc[j]) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + static_cast<int64_t>(j) * p.c));
+        }
+      }
+    }
     mbar_wait(&full_bar[stage], static_cast<uint32_t>((it / kNS) & 1));
     const T* st = tiles + stage * G::STAGE_ELEMS;
 #pragma unroll
@@ -513,11 +527,17 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
 #pragma unroll
       for (int i = 0; i < COLS + 3; ++i) ChanVec<T>::unpack(rowp[i * 8], q[i]);     // pixel pitch = 8 x 16 B
       if constexpr (SEP) {
+        // packed fp32 arithmetic (FFMA2: two channels per instruction) -- the bf16 variant is issue-bound otherwise
 #pragma unroll
         for (int j = 0; j < COLS; ++j)
 #pragma unroll
-          for (int k = 0; k < V; ++k)
-            hwin[rr][j][k] = fmaf(kv[3], q[j + 3][k], fmaf(kv[2], q[j + 2][k], fmaf(kv[1], q[j + 1][k], kv[0] * q[j][k])));
+          for (int k = 0; k < V; k += 2) {
+            float2 h = __fmul2_rn(make_float2(kv[0], kv[0]), make_float2(q[j][k], q[j][k + 1]));
+            h = __ffma2_rn(make_float2(kv[1], kv[1]), make_float2(q[j + 1][k], q[j + 1][k + 1]), h);
+            h = __ffma2_rn(make_float2(kv[2], kv[2]), make_float2(q[j + 2][k], q[j + 2][k + 1]), h);
+            h = __ffma2_rn(make_float2(kv[3], kv[3]), make_float2(q[j + 3][k], q[j + 3][k + 1]), h);
+            hwin[rr][j][k] = h.x; hwin[rr][j][k + 1] = h.y;
+          }
       } else {
 #pragma unroll
         for (int i = 0; i < COLS + 3; ++i)
@@ -532,10 +552,12 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
           float a4[V];
           if constexpr (SEP) {
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-              const float h0 = hwin[(rr + 1) & 3][j][k], h1 = hwin[(rr + 2) & 3][j][k];
-              const float h2 = hwin[(rr + 3) & 3][j][k], h3 = hwin[rr][j][k];       // rows r_in-3 .. r_in in order
-              a4[k] = fmaf(ku[3], h3, fmaf(ku[2], h2, fmaf(ku[1], h1, ku[0] * h0)));
+            for (int k = 0; k < V; k += 2) {      // rows r_in-3 .. r_in in order
+              float2 a = __fmul2_rn(make_float2(ku[0], ku[0]), make_float2(hwin[(rr + 1) & 3][j][k], hwin[(rr + 1) & 3][j][k + 1]));
+              a = __ffma2_rn(make_float2(ku[1], ku[1]), make_float2(hwin[(rr + 2) & 3][j][k], hwin[(rr + 2) & 3][j][k + 1]), a);
+              a = __ffma2_rn(make_float2(ku[2], ku[2]), make_float2(hwin[(rr + 3) & 3][j][k], hwin[(rr + 3) & 3][j][k + 1]), a);
+              a = __ffma2_rn(make_float2(ku[3], ku[3]), make_float2(hwin[rr][j][k], hwin[rr][j][k + 1]), a);
+              a4[k] = a.x; a4[k + 1] = a.y;
             }
           } else {
 #pragma unroll
@@ -552,11 +574,15 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
             const float nzj = nw * nzc[rr][j];
             float o2[V];
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-              float t = fmaf(a4[k], rq[k], bq[k] + nzj);
-              t = fast ? fmaxf(t, t * neg) : (t > 0.f ? t : t * neg) * p.gain;
-              a4[k] = t;
-              o2[k] = t * sq[k];
+            for (int k = 0; k < V; k += 2) {
+              float2 t = __ffma2_rn(make_float2(a4[k], a4[k + 1]), make_float2(rq[k], rq[k + 1]),
+                                    __fadd2_rn(make_float2(bq[k], bq[k + 1]), make_float2(nzj, nzj)));
+              const float2 tn = __fmul2_rn(t, make_float2(neg, neg));
+              if (fast) { t.x = fmaxf(t.x, tn.x); t.y = fmaxf(t.y, tn.y); }
+              else { t.x = (t.x > 0.f ? t.x : tn.x) * p.gain; t.y = (t.y > 0.f ? t.y : tn.y) * p.gain; }
+              const float2 o = __fmul2_rn(t, make_float2(sq[k], sq[k + 1]));
+              a4[k] = t.x; a4[k + 1] = t.y;
+              o2[k] = o.x; o2[k + 1] = o.y;
             }
             if (okc[j]) {
               if (out) *reinterpret_cast<uint4*>(out + ooff) = ChanVec<T>::pack(a4);

@@ -7,9 +7,14 @@
 //  * accumulators are interleaved per pixel -- slot 0 = sum of alpha, slots 1..C = sum of alpha*value[c],
 //    padded to a multiple of 4 floats -- so one footprint pixel receives ONE 16-byte vector reduction
 //    (red.global.add.v4.f32, sm_90+) per group of 4 slots instead of C+1 scalar atomics;
-//  * warp aggregation: consecutive points are spatial neighbours (callers splat rasterised masks), so lanes
-//    that target the same pixel in the same footprint step are combined with a segmented shuffle scan and
-//    only the last lane of each run issues the reduction;
+//  * warp aggregation ACROSS points (splat_torus_kernel, C <= 3): a warp walks a contiguous chunk of points, its lanes
+//    own the slots of a T x T torus of pixels (slot = (py mod T, px mod T), T >= the footprint extent) and keep the
+//    running sums of "their" pixel in registers while consecutive points keep hitting it -- callers splat rasterised
+//    masks in raster order, so a pixel collects all of its ~(footprint width x points per pixel) contributions in ONE
+//    lane and is flushed with ONE 16-byte reduction when the footprint window moves off it.  No shuffles, no
+//    match.any: the round-1 kernel (one lane per point, same-pixel lanes merged with a segmented shuffle scan per
+//    footprint step) spent more in the merge than it saved and was slower than the reference at sigma 1.3
+//    (profiles/r02_opbench_vs_reference_b32_before.txt); it is kept for C in 4..7;
 //  * normalisation (input + sum) / (alpha [clamped >= 1 if soft] + 1e-8) and the NCHW re-layout are one
 //    fused pass.
 // Float atomics make the summation order (hence the last bits) run-to-run dependent, exactly as in the
@@ -114,6 +119,85 @@ splat_scatter_kernel(float* __restrict__ acc, const float* __restrict__ coords, 
   }
 }
 
+// ---------------------------------------------------------------- torus accumulation (C <= 3: 4 accumulator slots per pixel)
+// T = torus side (4, 8 or 16), chosen per warp from sigma[n]: T >= 2*ceil(2*sigma) + 2 >= the footprint extent, so a
+// footprint never wraps onto itself.  A lane owns slots lane, lane + 32, ... (T*T/32 of them; 16 lanes idle when T == 4).
+constexpr int kMaxTorusSlots = 8;   // T = 16
+
+__global__ void __launch_bounds__(128)
+splat_torus_kernel(float* __restrict__ acc, const float* __restrict__ coords, const float* __restrict__ values,
+                   const float* __restrict__ sigma, SplatParams p, int chunk, int chunks_per_sample) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n = warp_id / chunks_per_sample;
+  if (n >= p.n) return;
+  const int64_t q0 = (warp_id - n * chunks_per_sample) * chunk;
+  const int64_t q1 = min(q0 + static_cast<int64_t>(chunk), p.points);
+  const float sd = __ldg(sigma + n);
+  const float len = 2.f * sd;
+  const float norm = -1.f / (2.f * sd * sd);
+  const int extent = static_cast<int>(floorf(2.f * len + 3.f));   // >= (b - t + 1) for every point
+  float* acc_n = acc + n * p.h * static_cast<int64_t>(p.w) * 4;
+  const float* cpt = coords + n * p.points * 2;
+  const float* vpt = values + n * p.points * p.c;
+  if (extent > 16) {
+    // very wide footprints: lanes stride over the window of each point, one reduction per (point, pixel)
+    for (int64_t q = q0; q < q1; ++q) {
+      const float x = __ldg(cpt + q * 2), y = __ldg(cpt + q * 2 + 1);
+      if (!(x >= 0.f && x < static_cast<float>(p.w) && y >= 0.f && y < static_cast<float>(p.h))) continue;
+      const int t = static_cast<int>(fmaxf(0.f, floorf(y - len))), b = static_cast<int>(fminf(static_cast<float>(p.h - 1), ceilf(y + len)));
+      const int l = static_cast<int>(fmaxf(0.f, floorf(x - len))), r = static_cast<int>(fminf(static_cast<float>(p.w - 1), ceilf(x + len)));
+      const int wd = r - l + 1, cnt = wd * (b - t + 1);
+      const float v0 = p.c > 0 ? __ldg(vpt + q * p.c) : 0.f, v1 = p.c > 1 ? __ldg(vpt + q * p.c + 1) : 0.f;
+      const float v2 = p.c > 2 ? __ldg(vpt + q * p.c + 2) : 0.f;
+      for (int e = lane; e < cnt; e += 32) {
+        const int py = t + e / wd, px = l + e % wd;
+        const float ddx = static_cast<float>(px) - x, ddy = static_cast<float>(py) - y;
+        const float a = expf(norm * (ddx * ddx + ddy * ddy));
+        red_add_v4(acc_n + (static_cast<int64_t>(py) * p.w + px) * 4, a, a * v0, a * v1, a * v2);
+      }
+    }
+    return;
+  }
+  const int T = extent <= 4 ? 4 : (extent <= 8 ? 8 : 16);
+  const int tmask = T - 1, tshift = (T == 4) ? 2 : (T == 8 ? 3 : 4);
+  const int nslots = (T * T + 31) / 32;
+  int hid[kMaxTorusSlots];
+  float a0[kMaxTorusSlots], a1[kMaxTorusSlots], a2[kMaxTorusSlots], a3[kMaxTorusSlots];
+#pragma unroll
+  for (int k = 0; k < kMaxTorusSlots; ++k) { hid[k] = -1; a0[k] = a1[k] = a2[k] = a3[k] = 0.f; }
+  for (int64_t q = q0; q < q1; ++q) {
+    const float x = __ldg(cpt + q * 2), y = __ldg(cpt + q * 2 + 1);          // warp-uniform (broadcast) loads
+    // points outside the image are ignored (splat_gpu_impl.cu:76); bounds: :78-81
+    if (!(x >= 0.f && x < static_cast<float>(p.w) && y >= 0.f && y < static_cast<float>(p.h))) continue;
+    const int t = static_cast<int>(fmaxf(0.f, floorf(y - len))), b = static_cast<int>(fminf(static_cast<float>(p.h - 1), ceilf(y + len)));
+    const int l = static_cast<int>(fmaxf(0.f, floorf(x - len))), r = static_cast<int>(fminf(static_cast<float>(p.w - 1), ceilf(x + len)));
+    const float v0 = p.c > 0 ? __ldg(vpt + q * p.c) : 0.f, v1 = p.c > 1 ? __ldg(vpt + q * p.c + 1) : 0.f;
+    const float v2 = p.c > 2 ? __ldg(vpt + q * p.c + 2) : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxTorusSlots; ++k) {
+      if (k < nslots) {
+        const int slot = lane + 32 * k;
+        const int sy = slot >> tshift, sx = slot & tmask;
+        const int px = l + ((sx - l) & tmask), py = t + ((sy - t) & tmask);   // the pixel of the window congruent to this slot
+        if (sy < T && px <= r && py <= b) {
+          const int id = py * p.w + px;
+          if (id != hid[k]) {
+            if (hid[k] >= 0) red_add_v4(acc_n + static_cast<int64_t>(hid[k]) * 4, a0[k], a1[k], a2[k], a3[k]);
+            hid[k] = id; a0[k] = a1[k] = a2[k] = a3[k] = 0.f;
+          }
+          const float ddx = static_cast<float>(px) - x, ddy = static_cast<float>(py) - y;
+          const float a = expf(norm * (ddx * ddx + ddy * ddy));
+          a0[k] += a; a1[k] = fmaf(a, v0, a1[k]); a2[k] = fmaf(a, v1, a2[k]); a3[k] = fmaf(a, v2, a3[k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxTorusSlots; ++k)
+    if (k < nslots && hid[k] >= 0) red_add_v4(acc_n + static_cast<int64_t>(hid[k]) * 4, a0[k], a1[k], a2[k], a3[k]);
+}
+
 // generic channel count: scalar atomics per slot (C > 7); still interleaved accumulators
 __global__ void __launch_bounds__(256)
 splat_scatter_generic_kernel(float* __restrict__ acc, const float* __restrict__ coords, const float* __restrict__ values,
@@ -196,7 +280,18 @@ int gg_splat2d_forward(float* out, void* workspace, const float* input, const fl
   const int64_t total = N * P;
   if (total > 0) {
     const int grid = splat_grid(total, 256);
-    if (p.slots == 4)
+    if (p.slots == 4 && static_cast<int64_t>(H) * W < 0x7fffffffLL) {
+      // points per warp: long enough to aggregate (a raster row of a dense mask revisits a pixel ~footprint x density
+      // times), short enough to fill the machine (~16 warps per SM)
+      int64_t chunk = (P + 16LL * sm_count() - 1) / (16LL * sm_count());
+      chunk = chunk < 64 ? 64 : (chunk > 512 ? 512 : chunk);
+      const int64_t cps = (P + chunk - 1) / chunk;
+      const int64_t warps = N * cps;
+      const int64_t blocks = (warps + 3) / 4;
+      if (blocks > 0x7fffffffLL || cps > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "splat2d: too many points");
+      splat_torus_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(acc, coordinates, values, sigma, p, static_cast<int>(chunk),
+                                                                       static_cast<int>(cps));
+    } else if (p.slots == 4)
       splat_scatter_kernel<1><<<grid, 256, 0, st>>>(acc, coordinates, values, sigma, p, total);
     else if (p.slots == 8)
       splat_scatter_kernel<2><<<grid, 256, 0, st>>>(acc, coordinates, values, sigma, p, total);

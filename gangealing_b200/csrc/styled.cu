@@ -45,42 +45,57 @@ struct TailFwdParams {
 // the three to-RGB rows) are staged once in shared memory; a group of 8 lanes owns 4 consecutive pixels per trip and walks
 // the channel vectors v = lane + 8j: 4 independent 16-byte loads in flight per lane, every constant fetched once per 4 pixels.
 template <typename T>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2)
 styled_tail_nhwc_kernel(const TailFwdParams p) {
   constexpr int V = ChanVec<T>::V;
-  extern __shared__ __align__(16) float cst[];         // [6][C]: d, b, s, w0, w1, w2
+  constexpr int Q = V / 4;                              // float4 quarters per channel vector
+  // constants of this sample, one plane per quarter so that lane l reads float4 #v of a plane (16-byte stride between the
+  // lanes of a group: conflict-free LDS.128): cst[k][q][nvec] float4, k = d, b, s, w0, w1, w2
+  extern __shared__ __align__(16) float cst[];
   const int C = p.C;
+  const int nvec = C / V, J = nvec / kGroup;
   const int64_t n = blockIdx.x / p.chunks_per_sample;
   const int ck = blockIdx.x - n * p.chunks_per_sample;
   const int64_t p0 = static_cast<int64_t>(ck) * p.chunk, p1 = min(p0 + p.chunk, p.hw);
   const bool fast = p.gain > 0.f && ((p.act == 3 && p.alpha >= 0.f && p.alpha <= 1.f) || p.act == 1);
   const float neg = (p.act == 3) ? p.alpha : 1.f;
   const float gfold = fast ? p.gain : 1.f;   // lrelu(t)*g == max(T, T*slope) with T = g*t: the gain folds into d, b, nw
-  float* dq = cst; float* bq = cst + C; float* sq = cst + 2 * C; float* wq = cst + 3 * C;
   for (int c = threadIdx.x; c < C; c += kT) {
-    dq[c] = (p.demod ? __ldg(p.demod + n * C + c) : 1.f) * gfold;
-    bq[c] = (p.bias ? __ldg(p.bias + c) : 0.f) * gfold;
-    sq[c] = p.s_next ? __ldg(p.s_next + n * C + c) : 1.f;
+    const int v = c / V, r = c - v * V, q = r >> 2, e = r & 3;
+    const int slot = (q * nvec + v) * 4 + e;            // plane k starts at k*C
+    cst[slot] = (p.demod ? __ldg(p.demod + n * C + c) : 1.f) * gfold;
+    cst[C + slot] = (p.bias ? __ldg(p.bias + c) : 0.f) * gfold;
+    cst[2 * C + slot] = p.s_next ? __ldg(p.s_next + n * C + c) : 1.f;
     if (p.rgb) {
-      wq[c] = __ldg(p.wm + (n * 3 + 0) * C + c);
-      wq[C + c] = __ldg(p.wm + (n * 3 + 1) * C + c);
-      wq[2 * C + c] = __ldg(p.wm + (n * 3 + 2) * C + c);
+      cst[3 * C + slot] = __ldg(p.wm + (n * 3 + 0) * C + c);
+      cst[4 * C + slot] = __ldg(p.wm + (n * 3 + 1) * C + c);
+      cst[5 * C + slot] = __ldg(p.wm + (n * 3 + 2) * C + c);
     }
   }
   const float nw = (p.noise ? (p.noise_weight ? __ldg(p.noise_weight) : 1.f) : 0.f) * gfold;
   __syncthreads();
+  const float4* c4 = reinterpret_cast<const float4*>(cst);
+  const int c4_plane = C / 4;                           // float4s per constant plane
   const int l = threadIdx.x & (kGroup - 1), grp = threadIdx.x / kGroup;
   const unsigned gmask = 0xffu << (threadIdx.x & 24);    // the groups of one warp may leave the loop at different trips
-  const int nvec = C / V, J = nvec / kGroup;
   const T* raw = static_cast<const T*>(p.raw);
   T* out = static_cast<T*>(p.out);
   T* xs = static_cast<T*>(p.xs);
-  for (int64_t pb = p0 + grp * kPix; pb < p1; pb += (kT / kGroup) * kPix) {
+  constexpr int64_t kStride = (kT / kGroup) * kPix;
+  // software pipeline over (trip, j): the 4 loads of step i+1 are issued before the arithmetic of step i
+  auto pixel = [&](int64_t pb_, int u) { return n * p.hw + min(pb_ + u, p1 - 1); };   // clamped: a tail pixel is recomputed, never stored
+  uint4 xn[kPix];
+  int64_t pb = p0 + grp * kPix;
+  if (pb < p1) {
+#pragma unroll
+    for (int u = 0; u < kPix; ++u) xn[u] = ldg_stream16(raw + (pixel(pb, u) * nvec + l) * V);
+  }
+  for (; pb < p1; pb += kStride) {
     float nz[kPix];
     int64_t pix[kPix];
 #pragma unroll
     for (int u = 0; u < kPix; ++u) {
-      pix[u] = n * p.hw + min(pb + u, p1 - 1);             // clamped: a tail pixel is recomputed, never stored
+      pix[u] = pixel(pb, u);
       nz[u] = p.noise ? nw * __ldg(p.noise + pix[u]) : 0.f;
     }
     float acc[kPix][3];
@@ -90,20 +105,25 @@ styled_tail_nhwc_kernel(const TailFwdParams p) {
       const int v = l + kGroup * j;
       uint4 xr[kPix];
 #pragma unroll
-      for (int u = 0; u < kPix; ++u) xr[u] = ldg_stream16(raw + (pix[u] * nvec + v) * V);
+      for (int u = 0; u < kPix; ++u) xr[u] = xn[u];
+      {  // prefetch the next step: (pb, j+1) or (pb + stride, 0)
+        const bool wrap = (j + 1 == J);
+        const int64_t pbn = wrap ? pb + kStride : pb;
+        const int vn = wrap ? l : v + kGroup;
+        if (pbn < p1) {
+#pragma unroll
+          for (int u = 0; u < kPix; ++u) xn[u] = ldg_stream16(raw + (pixel(pbn, u) * nvec + vn) * V);
+        }
+      }
       float d[V], b[V], s[V], w0[V], w1[V], w2[V];
 #pragma unroll
-      for (int q = 0; q < V / 4; ++q) {
-        const float4 dv = reinterpret_cast<const float4*>(dq)[v * (V / 4) + q];
-        const float4 bv = reinterpret_cast<const float4*>(bq)[v * (V / 4) + q];
-        const float4 sv = reinterpret_cast<const float4*>(sq)[v * (V / 4) + q];
+      for (int q = 0; q < Q; ++q) {
+        const float4 dv = c4[q * nvec + v], bv = c4[c4_plane + q * nvec + v], sv = c4[2 * c4_plane + q * nvec + v];
         d[4 * q] = dv.x; d[4 * q + 1] = dv.y; d[4 * q + 2] = dv.z; d[4 * q + 3] = dv.w;
         b[4 * q] = bv.x; b[4 * q + 1] = bv.y; b[4 * q + 2] = bv.z; b[4 * q + 3] = bv.w;
         s[4 * q] = sv.x; s[4 * q + 1] = sv.y; s[4 * q + 2] = sv.z; s[4 * q + 3] = sv.w;
         if (p.rgb) {
-          const float4 a0 = reinterpret_cast<const float4*>(wq)[v * (V / 4) + q];
-          const float4 a1 = reinterpret_cast<const float4*>(wq + C)[v * (V / 4) + q];
-          const float4 a2 = reinterpret_cast<const float4*>(wq + 2 * C)[v * (V / 4) + q];
+          const float4 a0 = c4[3 * c4_plane + q * nvec + v], a1 = c4[4 * c4_plane + q * nvec + v], a2 = c4[5 * c4_plane + q * nvec + v];
           w0[4 * q] = a0.x; w0[4 * q + 1] = a0.y; w0[4 * q + 2] = a0.z; w0[4 * q + 3] = a0.w;
           w1[4 * q] = a1.x; w1[4 * q + 1] = a1.y; w1[4 * q + 2] = a1.z; w1[4 * q + 3] = a1.w;
           w2[4 * q] = a2.x; w2[4 * q + 1] = a2.y; w2[4 * q + 2] = a2.z; w2[4 * q + 3] = a2.w;

@@ -13,10 +13,44 @@ from .heads import FlowHead, SimilarityHead
 from .sampling import BilinearDownsample
 
 
+class _TVLoss(torch.autograd.Function):
+    """total_variation_loss(reduce_batch=True) as one reduction kernel per direction (csrc/optim.cu)."""
+
+    @staticmethod
+    def forward(ctx, flow):
+        from .. import _lib
+        f = flow.detach()
+        if f.dtype != torch.float32 or not f.is_contiguous():
+            f = f.float().contiguous()
+        n, h, w, _ = f.shape
+        lib = _lib.load()
+        out = torch.empty(1, dtype=torch.float32, device=f.device)
+        ws = torch.empty(max(1, lib.gg_tv_loss_workspace(n, h, w) // 4), dtype=torch.float32, device=f.device)
+        _lib.check(lib.gg_tv_loss_forward(out.data_ptr(), ws.data_ptr(), f.data_ptr(), n, h, w, _lib.stream()), "gg_tv_loss_forward")
+        ctx.save_for_backward(f)
+        ctx.dtype = flow.dtype
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import _lib
+        (f,) = ctx.saved_tensors
+        n, h, w, _ = f.shape
+        go = g.detach().float().reshape(1).contiguous()
+        grad = torch.empty_like(f)
+        _lib.check(_lib.load().gg_tv_loss_backward(grad.data_ptr(), go.data_ptr(), f.data_ptr(), n, h, w, _lib.stream()),
+                   "gg_tv_loss_backward")
+        return grad.to(ctx.dtype)
+
+
 def total_variation_loss(delta_flow, reduce_batch=True):
-    """Huber-penalised finite differences of a (N, H, W, 2) residual flow (reference models/losses/loss.py:4-12)."""
+    """Huber-penalised finite differences of a (N, H, W, 2) residual flow (reference models/losses/loss.py:4-12).
+    On CUDA the batch-reduced form (the training loss) is one fused reduction kernel forward and one gather kernel backward;
+    the per-sample form (forward_with_flip's tie-break) and CPU tensors (the oracle's legs) use the tensor formulation."""
     dims = (0, 1, 2, 3) if reduce_batch else (1, 2, 3)
     assert delta_flow.size(-1) == 2
+    if reduce_batch and delta_flow.is_cuda and delta_flow.dim() == 4 and delta_flow.size(1) > 1 and delta_flow.size(2) > 1:
+        return _TVLoss.apply(delta_flow)
 
     def huber(a):
         return torch.where(a <= 1.0, 0.5 * a.pow(2), a - 0.5).mean(dim=dims)

@@ -62,6 +62,7 @@ class TrainConfig:
     dtype: str = "f32"                # "f32" (BASELINE config 2) or "bf16" (config 3): STORAGE type of the generator / STN
     #                                   trunk / VGG activations; fp32 master weights, fp32 arithmetic in the fused kernels,
     #                                   bf16 tensor-core convolutions, fp32 images / grids / losses / optimiser
+    fused_optimizer: bool = True      # CUDA: Adam x2 + EMA as ONE multi-tensor kernel (training/fused_optim.py)
     grad_compression: str = "none"    # DDP gradient all-reduce: "none" (fp32) or "bf16" (compressed on the wire)
     bucket_cap_mb: int = 25
 
@@ -133,14 +134,28 @@ class Trainer:
         # serves the whole schedule (psi 1 -> 0, cyclic lr: reference train.py:89-96,129-132); `step(psi=, lr=, ll_lr=)`
         # copies new values into these scalars before the replay
         self.psi_t = torch.tensor(float(cfg.psi), device=device)
-        self.stn_lr_t = torch.tensor(float(cfg.stn_lr), device=device) if fused else None
-        self.ll_lr_t = torch.tensor(float(cfg.ll_lr), device=device) if fused else None
-        self.t_optim = optim.Adam(self.t_module.parameters(), lr=self.stn_lr_t if fused else cfg.stn_lr, betas=(0.9, 0.999),
-                                  eps=1e-8, fused=fused, capturable=fused)
-        self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=self.ll_lr_t if fused else cfg.ll_lr, betas=(0.9, 0.999),
-                                   eps=1e-8, fused=fused, capturable=fused)
-        self._graph = None
         self.accum = 0.5 ** (32 / (10 * 1000))
+        self.fused_optim = None
+        if fused and ops is None and cfg.fused_optimizer:
+            # train.py:126-134 in one kernel: Adam for the STN and the latent learner + the EMA of the STN
+            from .fused_optim import FusedAdamEMA
+            groups = [{"params": list(self.t_module.parameters()), "lr": cfg.stn_lr}]
+            if not cfg.freeze_ll:
+                groups.append({"params": list(self.ll_module.parameters()), "lr": cfg.ll_lr})
+            ema = dict(self.t_ema.named_parameters())
+            pairs = {p: ema[k] for k, p in self.t_module.named_parameters()}
+            self.fused_optim = FusedAdamEMA(groups, betas=(0.9, 0.999), eps=1e-8, ema_pairs=pairs, ema_decay=self.accum)
+            self.t_optim = self.ll_optim = self.fused_optim
+            self.stn_lr_t = self.fused_optim.lr_tensor(0)
+            self.ll_lr_t = self.fused_optim.lr_tensor(1) if not cfg.freeze_ll else None
+        else:
+            self.stn_lr_t = torch.tensor(float(cfg.stn_lr), device=device) if fused else None
+            self.ll_lr_t = torch.tensor(float(cfg.ll_lr), device=device) if fused else None
+            self.t_optim = optim.Adam(self.t_module.parameters(), lr=self.stn_lr_t if fused else cfg.stn_lr, betas=(0.9, 0.999),
+                                      eps=1e-8, fused=fused, capturable=fused)
+            self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=self.ll_lr_t if fused else cfg.ll_lr, betas=(0.9, 0.999),
+                                       eps=1e-8, fused=fused, capturable=fused)
+        self._graph = None
         self.zero = torch.tensor(0.0, device=device)
         # each rank draws its own latents (reference train.py:193: seed*world + rank)
         torch.manual_seed(cfg.seed * max(1, gdist.get_world_size()) + gdist.get_rank() + seed_offset)
@@ -171,7 +186,7 @@ class Trainer:
                 continue
             if scalar is not None:
                 scalar.fill_(value) if not torch.is_tensor(value) else scalar.copy_(value, non_blocking=True)
-            else:
+            elif optimiser is not self.fused_optim:
                 for group in optimiser.param_groups:
                     group["lr"] = float(value)
 
@@ -235,10 +250,13 @@ class Trainer:
         self.ll_optim.zero_grad(set_to_none=True)
         full = loss_dict["p"] + cfg.tv_weight * loss_dict["tv"] + cfg.flow_identity_weight * loss_dict["f"]
         full.backward()
-        self.t_optim.step()
-        if not cfg.freeze_ll:
-            self.ll_optim.step()
-        accumulate(self.t_ema, self.t_module, self.accum)
+        if self.fused_optim is not None:
+            self.fused_optim.step()               # Adam (both groups) + EMA: one multi-tensor kernel
+        else:
+            self.t_optim.step()
+            if not cfg.freeze_ll:
+                self.ll_optim.step()
+            accumulate(self.t_ema, self.t_module, self.accum)
         # detached: a caller that keeps the returned dict must not keep the iteration's autograd graph (and its
         # AccumulateGrad nodes, which are pinned to the stream they were created on) alive
         return gdist.reduce_loss_dict({k: v.detach() for k, v in loss_dict.items()})

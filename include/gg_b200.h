@@ -351,6 +351,24 @@ GG_API int gg_tent_downsample_forward(float* out, const float* in, const float* 
 GG_API int gg_tent_downsample_backward(float* grad_in, const float* grad_out, const float* taps_h, const float* taps_v,
                                        int64_t N, int C, int in_h, int in_w, int stride, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training-loop bookkeeping, csrc/optim.cu.
+ *   gg_adam_ema_step: reference train.py:126-134 -- torch.optim.Adam.step() for every parameter of both optimisers and the
+ *     EMA `accumulate(t_ema, t_module)` (models/__init__.py:19-24) -- as one multi-tensor pass.
+ *     table: DEVICE array of rows {float* p; const float* g; float* m; float* v; float* ema (may be NULL); int64 numel;
+ *     const float* lr (device scalar)}; block_tensor / block_chunk: DEVICE int arrays of `blocks` entries mapping a CTA to
+ *     (table row, chunk of `chunk` elements); state: DEVICE float[3] = {step, 1 - b1^step, sqrt(1 - b2^step)} -- the call
+ *     increments step first (torch's default Adam arithmetic: m, v, step_size = lr/bc1, denom = sqrt(v)/sqrt(bc2) + eps).
+ *   gg_tv_loss_forward/backward: reference models/losses/loss.py:4-12 total_variation_loss(delta_flow (N, H, W, 2)),
+ *     reduce_batch=True: out[0] = mean huber|d/dy| + mean huber|d/dx|; backward is gather-form (deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int gg_adam_ema_step(const void* table, const int* block_tensor, const int* block_chunk, int blocks, int chunk,
+                            float* state, float beta1, float beta2, float eps, float ema_decay, void* stream);
+GG_API int64_t gg_tv_loss_workspace(int64_t N, int H, int W);
+GG_API int gg_tv_loss_forward(float* out, void* workspace, const float* flow, int64_t N, int H, int W, void* stream);
+GG_API int gg_tv_loss_backward(float* grad_flow, const float* grad_out, const float* flow, int64_t N, int H, int W,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
