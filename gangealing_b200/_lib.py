@@ -58,7 +58,10 @@ SIGNATURES = {
     "gg_to_rgb_nhwc_workspace": (_L, [_L, _I, _L]),
     "gg_to_rgb_nhwc_forward": (_I, [_P] * 5 + [_L, _I, _L, _P]),
     "gg_to_rgb_nhwc_backward": (_I, [_P] * 6 + [_L, _I, _L, _P]),
-    "gg_adam_ema_step": (_I, [_P, _P, _P, _I, _I, _P, _F, _F, _F, _F, _P]),
+    "gg_nn_argmin_workspace": (_L, [_L, _L]),
+    "gg_nn_argmin": (_I, [_P, _P, _P, _P, _L, _L, _I, _P]),
+    "gg_splat2d_lookup_forward": (_I, [_P] * 8 + [_L, _L, _I, _I, _I, _I, _I, _F, _F, _I, _P]),
+    "gg_adam_ema_step": (_I, [_P, _P, _P, _I, _I, _P, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _P]),
     "gg_tv_loss_workspace": (_L, [_L, _I, _I]),
     "gg_tv_loss_forward": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "gg_tv_loss_backward": (_I, [_P, _P, _P, _L, _I, _I, _P]),

@@ -24,27 +24,28 @@ struct AdamTensor {          // one row of the device-resident table (7 x 8 byte
   const float* lr;           // device scalar of this tensor's parameter group
 };
 
-__global__ void adam_tick_kernel(float* __restrict__ state, float beta1, float beta2) {
+__global__ void adam_tick_kernel(float* __restrict__ state, double beta1, double beta2) {
   // state[0] = step (as float, exact up to 2^24), state[1] = 1 - b1^t, state[2] = sqrt(1 - b2^t)
   const float t = state[0] + 1.f;
   state[0] = t;
-  state[1] = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(t)));
-  state[2] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(t))));
+  state[1] = static_cast<float>(1.0 - pow(beta1, static_cast<double>(t)));
+  state[2] = static_cast<float>(sqrt(1.0 - pow(beta2, static_cast<double>(t))));
 }
 
 constexpr int kAdamThreads = 256;
 
 __global__ void __launch_bounds__(kAdamThreads)
 adam_ema_kernel(const AdamTensor* __restrict__ table, const int* __restrict__ block_tensor,
-                const int* __restrict__ block_chunk, const float* __restrict__ state, float beta1, float beta2, float eps,
-                float decay, int chunk) {
+                const int* __restrict__ block_chunk, const float* __restrict__ state, float omb1, float beta2, float omb2,
+                float eps, float decay, float omd, int chunk) {
+  // omb1 = 1 - beta1, omb2 = 1 - beta2, omd = 1 - decay are formed in double precision on the host (1 - 0.999f in fp32
+  // would be off by 5e-5 relative)
   const AdamTensor t = table[block_tensor[blockIdx.x]];
   const int64_t e0 = static_cast<int64_t>(block_chunk[blockIdx.x]) * chunk;
   const int64_t e1 = min(e0 + static_cast<int64_t>(chunk), t.numel);
   const float lr = __ldg(t.lr);
   const float step_size = lr / state[1];
   const float inv_bc2 = 1.f / state[2];
-  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2, omd = 1.f - decay;
   const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) | reinterpret_cast<uintptr_t>(t.m) |
                      reinterpret_cast<uintptr_t>(t.v) | reinterpret_cast<uintptr_t>(t.ema)) & 15) == 0 && (e0 & 3) == 0;
   auto upd = [&](float& p, float g, float& m, float& v, float& e) {
@@ -167,17 +168,20 @@ using namespace gg;
 extern "C" {
 
 int gg_adam_ema_step(const void* table, const int* block_tensor, const int* block_chunk, int blocks, int chunk,
-                     float* state, float beta1, float beta2, float eps, float ema_decay, void* stream) {
+                     float* state, double beta1, double beta2, double eps, double ema_decay, void* stream) {
   if (blocks < 0 || chunk < 1) return fail(GG_ERR_BAD_ARG, "adam_ema_step: bad geometry");
   if (!state) return fail(GG_ERR_BAD_ARG, "adam_ema_step: null state");
-  if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f)) return fail(GG_ERR_BAD_ARG, "adam_ema_step: bad hyper-parameters");
+  if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0)) return fail(GG_ERR_BAD_ARG, "adam_ema_step: bad hyper-parameters");
   auto st = static_cast<cudaStream_t>(stream);
   adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
   GG_CHECK_LAUNCH("adam_tick launch");
   if (blocks == 0) return GG_OK;
   if (!table || !block_tensor || !block_chunk) return fail(GG_ERR_BAD_ARG, "adam_ema_step: null table");
   adam_ema_kernel<<<static_cast<unsigned>(blocks), kAdamThreads, 0, st>>>(static_cast<const AdamTensor*>(table), block_tensor,
-                                                                         block_chunk, state, beta1, beta2, eps, ema_decay, chunk);
+                                                                         block_chunk, state, static_cast<float>(1.0 - beta1),
+                                                                         static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
+                                                                         static_cast<float>(eps), static_cast<float>(ema_decay),
+                                                                         static_cast<float>(1.0 - ema_decay), chunk);
   GG_CHECK_LAUNCH("adam_ema launch");
   return GG_OK;
 }

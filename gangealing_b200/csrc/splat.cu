@@ -124,9 +124,45 @@ splat_scatter_kernel(float* __restrict__ acc, const float* __restrict__ coords, 
 // footprint never wraps onto itself.  A lane owns slots lane, lane + 32, ... (T*T/32 of them; 16 lanes idle when T == 4).
 constexpr int kMaxTorusSlots = 8;   // T = 16
 
+// LOOKUP (reference spatial_transformer.py:141-157 `uncongeal_points` + helpers.py:178-187): the
+// points arrive as QUERY coordinates in the congealed frame; their image positions are looked up in the STN's sampling
+// grid -- F.grid_sample(grid as a 2-channel image, query, 'border', align_corners=False) -- and un-normalised to pixels
+// (spatial_transformer.py:621-623) as the points are loaded, instead of a grid_sample launch + 4 elementwise launches.
+struct LookupParams {
+  const float* grid;     // (N, gh, gw, 2)
+  int gh, gw;
+  float k, m;            // unnormalize: ((g / k) / 2 + 0.5) * m,  k = (res-1)/res, m = out_res - 1
+  float* points_out;     // (N, P, 2) or null: the looked-up pixel coordinates
+};
+
+__device__ __forceinline__ float2 lookup_point(const LookupParams& lk, int64_t n, float qx, float qy) {
+  // ATen grid_sampler_2d, bilinear, padding_mode=border, align_corners=False
+  float ix = ((qx + 1.f) * lk.gw - 1.f) / 2.f, iy = ((qy + 1.f) * lk.gh - 1.f) / 2.f;
+  ix = fminf(fmaxf(ix, 0.f), static_cast<float>(lk.gw - 1));
+  iy = fminf(fmaxf(iy, 0.f), static_cast<float>(lk.gh - 1));
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  const float* g = lk.grid + n * lk.gh * static_cast<int64_t>(lk.gw) * 2;
+  float ox = 0.f, oy = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int yy = y0 + a, xx = x0 + b;
+      if (yy >= 0 && yy < lk.gh && xx >= 0 && xx < lk.gw) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(g + (static_cast<int64_t>(yy) * lk.gw + xx) * 2));
+        const float w = (a ? wy1 : wy0) * (b ? wx1 : wx0);
+        ox = fmaf(v.x, w, ox); oy = fmaf(v.y, w, oy);
+      }
+    }
+  return make_float2(((ox / lk.k) / 2.f + 0.5f) * lk.m, ((oy / lk.k) / 2.f + 0.5f) * lk.m);
+}
+
+template <bool LOOKUP>
 __global__ void __launch_bounds__(128)
 splat_torus_kernel(float* __restrict__ acc, const float* __restrict__ coords, const float* __restrict__ values,
-                   const float* __restrict__ sigma, SplatParams p, int chunk, int chunks_per_sample) {
+                   const float* __restrict__ sigma, SplatParams p, int chunk, int chunks_per_sample, LookupParams lk) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n = warp_id / chunks_per_sample;
@@ -143,7 +179,12 @@ splat_torus_kernel(float* __restrict__ acc, const float* __restrict__ coords, co
   if (extent > 16) {
     // very wide footprints: lanes stride over the window of each point, one reduction per (point, pixel)
     for (int64_t q = q0; q < q1; ++q) {
-      const float x = __ldg(cpt + q * 2), y = __ldg(cpt + q * 2 + 1);
+      float x = __ldg(cpt + q * 2), y = __ldg(cpt + q * 2 + 1);
+      if (LOOKUP) {
+        const float2 pp = lookup_point(lk, n, x, y);
+        x = pp.x; y = pp.y;
+        if (lk.points_out && lane == 0) *reinterpret_cast<float2*>(lk.points_out + (n * p.points + q) * 2) = pp;
+      }
       if (!(x >= 0.f && x < static_cast<float>(p.w) && y >= 0.f && y < static_cast<float>(p.h))) continue;
       const int t = static_cast<int>(fmaxf(0.f, floorf(y - len))), b = static_cast<int>(fminf(static_cast<float>(p.h - 1), ceilf(y + len)));
       const int l = static_cast<int>(fmaxf(0.f, floorf(x - len))), r = static_cast<int>(fminf(static_cast<float>(p.w - 1), ceilf(x + len)));
@@ -161,34 +202,57 @@ splat_torus_kernel(float* __restrict__ acc, const float* __restrict__ coords, co
   }
   const int T = extent <= 4 ? 4 : (extent <= 8 ? 8 : 16);
   const int tmask = T - 1, tshift = (T == 4) ? 2 : (T == 8 ? 3 : 4);
-  const int nslots = (T * T + 31) / 32;
+  // T == 4: 16 slots -- the two half-warps run two independent tori on alternate points (a pixel held by both is simply
+  // flushed twice); otherwise T*T/32 slots per lane
+  const int npar = (T == 4) ? 2 : 1;
+  const int sub = (T == 4) ? (lane >> 4) : 0;
+  const int lane_slot = (T == 4) ? (lane & 15) : lane;
+  const int nslots = (T == 4) ? 1 : (T * T) / 32;
   int hid[kMaxTorusSlots];
   float a0[kMaxTorusSlots], a1[kMaxTorusSlots], a2[kMaxTorusSlots], a3[kMaxTorusSlots];
 #pragma unroll
   for (int k = 0; k < kMaxTorusSlots; ++k) { hid[k] = -1; a0[k] = a1[k] = a2[k] = a3[k] = 0.f; }
-  for (int64_t q = q0; q < q1; ++q) {
-    const float x = __ldg(cpt + q * 2), y = __ldg(cpt + q * 2 + 1);          // warp-uniform (broadcast) loads
-    // points outside the image are ignored (splat_gpu_impl.cu:76); bounds: :78-81
-    if (!(x >= 0.f && x < static_cast<float>(p.w) && y >= 0.f && y < static_cast<float>(p.h))) continue;
-    const int t = static_cast<int>(fmaxf(0.f, floorf(y - len))), b = static_cast<int>(fminf(static_cast<float>(p.h - 1), ceilf(y + len)));
-    const int l = static_cast<int>(fmaxf(0.f, floorf(x - len))), r = static_cast<int>(fminf(static_cast<float>(p.w - 1), ceilf(x + len)));
-    const float v0 = p.c > 0 ? __ldg(vpt + q * p.c) : 0.f, v1 = p.c > 1 ? __ldg(vpt + q * p.c + 1) : 0.f;
-    const float v2 = p.c > 2 ? __ldg(vpt + q * p.c + 2) : 0.f;
+  for (int64_t qb = q0; qb < q1; qb += 32) {
+    // one coalesced load per lane fetches 32 points; they are then broadcast with shuffles (no per-point load latency)
+    const int64_t ql = qb + lane;
+    float lx = -1.f, ly = -1.f, lv0 = 0.f, lv1 = 0.f, lv2 = 0.f;
+    if (ql < q1) {
+      float2 xy = __ldg(reinterpret_cast<const float2*>(cpt + ql * 2));
+      if (LOOKUP) {
+        xy = lookup_point(lk, n, xy.x, xy.y);
+        if (lk.points_out) *reinterpret_cast<float2*>(lk.points_out + (n * p.points + ql) * 2) = xy;
+      }
+      lx = xy.x; ly = xy.y;
+      if (p.c > 0) lv0 = __ldg(vpt + ql * p.c);
+      if (p.c > 1) lv1 = __ldg(vpt + ql * p.c + 1);
+      if (p.c > 2) lv2 = __ldg(vpt + ql * p.c + 2);
+    }
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(32), q1 - qb));
+    for (int i = 0; i < cnt; i += npar) {
+      const int src = min(i + sub, 31);
+      const float x = __shfl_sync(0xffffffffu, lx, src), y = __shfl_sync(0xffffffffu, ly, src);
+      const float v0 = __shfl_sync(0xffffffffu, lv0, src), v1 = __shfl_sync(0xffffffffu, lv1, src);
+      const float v2 = __shfl_sync(0xffffffffu, lv2, src);
+      // points outside the image are ignored (splat_gpu_impl.cu:76); bounds: :78-81
+      if (i + sub >= cnt || !(x >= 0.f && x < static_cast<float>(p.w) && y >= 0.f && y < static_cast<float>(p.h))) continue;
+      const int t = static_cast<int>(fmaxf(0.f, floorf(y - len))), b = static_cast<int>(fminf(static_cast<float>(p.h - 1), ceilf(y + len)));
+      const int l = static_cast<int>(fmaxf(0.f, floorf(x - len))), r = static_cast<int>(fminf(static_cast<float>(p.w - 1), ceilf(x + len)));
 #pragma unroll
-    for (int k = 0; k < kMaxTorusSlots; ++k) {
-      if (k < nslots) {
-        const int slot = lane + 32 * k;
-        const int sy = slot >> tshift, sx = slot & tmask;
-        const int px = l + ((sx - l) & tmask), py = t + ((sy - t) & tmask);   // the pixel of the window congruent to this slot
-        if (sy < T && px <= r && py <= b) {
-          const int id = py * p.w + px;
-          if (id != hid[k]) {
-            if (hid[k] >= 0) red_add_v4(acc_n + static_cast<int64_t>(hid[k]) * 4, a0[k], a1[k], a2[k], a3[k]);
-            hid[k] = id; a0[k] = a1[k] = a2[k] = a3[k] = 0.f;
+      for (int k = 0; k < kMaxTorusSlots; ++k) {
+        if (k < nslots) {
+          const int slot = lane_slot + 32 * k;
+          const int sy = slot >> tshift, sx = slot & tmask;
+          const int px = l + ((sx - l) & tmask), py = t + ((sy - t) & tmask);   // the pixel of the window congruent to this slot
+          if (px <= r && py <= b) {
+            const int id = py * p.w + px;
+            if (id != hid[k]) {
+              if (hid[k] >= 0) red_add_v4(acc_n + static_cast<int64_t>(hid[k]) * 4, a0[k], a1[k], a2[k], a3[k]);
+              hid[k] = id; a0[k] = a1[k] = a2[k] = a3[k] = 0.f;
+            }
+            const float ddx = static_cast<float>(px) - x, ddy = static_cast<float>(py) - y;
+            const float a = expf(norm * (ddx * ddx + ddy * ddy));
+            a0[k] += a; a1[k] = fmaf(a, v0, a1[k]); a2[k] = fmaf(a, v1, a2[k]); a3[k] = fmaf(a, v2, a3[k]);
           }
-          const float ddx = static_cast<float>(px) - x, ddy = static_cast<float>(py) - y;
-          const float a = expf(norm * (ddx * ddx + ddy * ddy));
-          a0[k] += a; a1[k] = fmaf(a, v0, a1[k]); a2[k] = fmaf(a, v1, a2[k]); a3[k] = fmaf(a, v2, a3[k]);
         }
       }
     }
@@ -262,9 +326,9 @@ int64_t gg_splat2d_workspace(int64_t N, int C, int H, int W) {
   return N * H * static_cast<int64_t>(W) * slots * static_cast<int64_t>(sizeof(float));
 }
 
-int gg_splat2d_forward(float* out, void* workspace, const float* input, const float* coordinates, const float* values,
-                       const float* sigma, int64_t N, int64_t P, int C, int H, int W, int soft_normalize,
-                       void* stream) {
+static int splat_impl(float* out, void* workspace, const float* input, const float* coordinates, const float* values,
+                      const float* sigma, int64_t N, int64_t P, int C, int H, int W, int soft_normalize, const LookupParams* lk,
+                      void* stream) {
   if (N < 0 || P < 0 || C < 0 || H < 0 || W < 0) return fail(GG_ERR_BAD_ARG, "splat2d: negative size");
   const int64_t numel = N * C * H * static_cast<int64_t>(W);
   if (numel == 0) return GG_OK;  // reference returns the (empty) clone (splat_gpu.c:23-26)
@@ -274,6 +338,8 @@ int gg_splat2d_forward(float* out, void* workspace, const float* input, const fl
   SplatParams p;
   p.n = N; p.points = P; p.c = C; p.h = H; p.w = W;
   p.slots = ((C + 1) + 3) / 4 * 4;
+  if (lk && (p.slots != 4 || static_cast<int64_t>(H) * W >= 0x7fffffffLL))
+    return fail(GG_ERR_UNSUPPORTED, "splat2d_lookup: the fused lookup serves C <= 3 (the call sites splat RGB colours or a 1-channel mask)");
   cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(gg_splat2d_workspace(N, C, H, W)), st);
   if (e != cudaSuccess) return cuda_fail(e, "splat2d workspace memset");
   float* acc = static_cast<float*>(workspace);
@@ -289,8 +355,12 @@ int gg_splat2d_forward(float* out, void* workspace, const float* input, const fl
       const int64_t warps = N * cps;
       const int64_t blocks = (warps + 3) / 4;
       if (blocks > 0x7fffffffLL || cps > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "splat2d: too many points");
-      splat_torus_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(acc, coordinates, values, sigma, p, static_cast<int>(chunk),
-                                                                       static_cast<int>(cps));
+      if (lk)
+        splat_torus_kernel<true><<<static_cast<unsigned>(blocks), 128, 0, st>>>(acc, coordinates, values, sigma, p, static_cast<int>(chunk),
+                                                                               static_cast<int>(cps), *lk);
+      else
+        splat_torus_kernel<false><<<static_cast<unsigned>(blocks), 128, 0, st>>>(acc, coordinates, values, sigma, p, static_cast<int>(chunk),
+                                                                                static_cast<int>(cps), LookupParams{});
     } else if (p.slots == 4)
       splat_scatter_kernel<1><<<grid, 256, 0, st>>>(acc, coordinates, values, sigma, p, total);
     else if (p.slots == 8)
@@ -302,6 +372,23 @@ int gg_splat2d_forward(float* out, void* workspace, const float* input, const fl
   splat_normalize_kernel<<<splat_grid(numel, 256), 256, 0, st>>>(out, input, acc, p, soft_normalize ? 1 : 0, numel);
   GG_CHECK_LAUNCH("splat_normalize launch");
   return GG_OK;
+}
+
+int gg_splat2d_forward(float* out, void* workspace, const float* input, const float* coordinates, const float* values,
+                       const float* sigma, int64_t N, int64_t P, int C, int H, int W, int soft_normalize,
+                       void* stream) {
+  return splat_impl(out, workspace, input, coordinates, values, sigma, N, P, C, H, W, soft_normalize, nullptr, stream);
+}
+
+int gg_splat2d_lookup_forward(float* out, float* points_out, void* workspace, const float* input, const float* grid,
+                              const float* query, const float* values, const float* sigma, int64_t N, int64_t P, int C,
+                              int H, int W, int grid_h, int grid_w, float unnorm_k, float unnorm_m, int soft_normalize,
+                              void* stream) {
+  if (grid_h < 1 || grid_w < 1 || !(unnorm_k != 0.f)) return fail(GG_ERR_BAD_ARG, "splat2d_lookup: bad grid geometry");
+  if (N * P > 0 && !grid) return fail(GG_ERR_BAD_ARG, "splat2d_lookup: null grid");
+  LookupParams lk;
+  lk.grid = grid; lk.gh = grid_h; lk.gw = grid_w; lk.k = unnorm_k; lk.m = unnorm_m; lk.points_out = points_out;
+  return splat_impl(out, workspace, input, query, values, sigma, N, P, C, H, W, soft_normalize, &lk, stream);
 }
 
 }  // extern "C"

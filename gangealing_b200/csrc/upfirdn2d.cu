@@ -62,12 +62,23 @@ upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ in, const fl
   if (FUSED) nw = ep.noise ? (ep.noise_weight ? __ldg(ep.noise_weight) : 1.f) : 0.f;
   // out[m, oy, ox] = sum_{ky,kx} U[oy*dy + ky, ox*dx + kx] * taps[kh-1-ky][kw-1-kx]
   // U = zero-inserted, padded input: U[y, x] = in[(y-pad_y0)/up_y, (x-pad_x0)/up_x] when divisible & in range.
+  const bool small = total <= 0x7fffffffLL;     // 32-bit index arithmetic (a 64-bit div/mod pair costs more than the taps)
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ox = static_cast<int>(idx % p.out_w);
-    const int64_t t = idx / p.out_w;
-    const int oy = static_cast<int>(t % p.out_h);
-    const int64_t m = t / p.out_h;
+    int ox, oy;
+    int64_t m;
+    if (small) {
+      const unsigned i32 = static_cast<unsigned>(idx), t32 = i32 / static_cast<unsigned>(p.out_w);
+      ox = static_cast<int>(i32 - t32 * static_cast<unsigned>(p.out_w));
+      const unsigned m32 = t32 / static_cast<unsigned>(p.out_h);
+      oy = static_cast<int>(t32 - m32 * static_cast<unsigned>(p.out_h));
+      m = m32;
+    } else {
+      ox = static_cast<int>(idx % p.out_w);
+      const int64_t t = idx / p.out_w;
+      oy = static_cast<int>(t % p.out_h);
+      m = t / p.out_h;
+    }
     const int y0 = oy * p.down_y - p.pad_y0;  // U-row of ky = 0, in input*up coordinates
     const int x0 = ox * p.down_x - p.pad_x0;
     const int iy_lo = max(ceildiv_s(y0, p.up_y), 0);

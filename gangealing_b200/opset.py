@@ -17,7 +17,9 @@ def cuda_ops():
         from .op import modconv as _mod
         from .stn import flow as _flow
         from .stn import sampling as _smp
+        from .splat2d import nn_argmin as _nn_argmin
         from .splat2d import splat2d as _splat2d
+        from .splat2d import splat2d_lookup as _splat2d_lookup
         from .op import feature_distance as _fd
         _cached = types.SimpleNamespace(
             name="sm_100a",
@@ -37,6 +39,8 @@ def cuda_ops():
             stn_sample_affine=_smp.stn_sample_affine,     # one-pass sampling (grid generated inside the sampler)
             stn_sample_flow=_smp.stn_sample_flow,
             splat2d=_splat2d,
+            splat2d_lookup=_splat2d_lookup,               # uncongeal_points' grid lookup fused into the splat
+            nn_argmin=_nn_argmin,                         # congeal_points' brute-force search without the distance tensor
             feature_distance=_fd.feature_distance,
         )
     return _cached

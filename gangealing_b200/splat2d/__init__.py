@@ -1,9 +1,9 @@
 """Mirror of reference utils/splat2d_cuda/__init__.py (`from .splat import *`)."""
 import torch.nn as nn
 
-from .functional import splat2d
+from .functional import nn_argmin, splat2d, splat2d_lookup
 
-__all__ = ["Splat2D", "splat2d"]
+__all__ = ["Splat2D", "splat2d", "splat2d_lookup", "nn_argmin"]
 
 
 class Splat2D(nn.Module):

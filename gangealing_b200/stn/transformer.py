@@ -234,11 +234,17 @@ class SpatialTransformer(nn.Module):
                 congealed = self.unnormalize(congealed, source_res, source_res)
         else:  # brute-force nearest neighbour on the reverse sampling grid
             assert fmA.size(-1) == 2
-            g = (fmA + self.identity_flow).reshape(n, fmA.size(1), fmA.size(2), 1, 1, 2)
-            pts = pointsA.reshape(n, 1, 1, num_points, 2, 1)
-            sim = (g @ pts)[..., 0, 0]
-            dist = pts.pow(2).squeeze(-1).sum(dim=-1) + g.pow(2).sum(dim=-1).squeeze(-1) - 2 * sim
-            nearest = dist.reshape(n, g.size(1) * g.size(2), num_points).argmin(dim=1)
+            g = fmA + self.identity_flow                                   # (N, H, W, 2)
+            fused = getattr(self.ops, "nn_argmin", None)
+            if fused is not None and g.is_cuda:
+                # tiled argmin kernel (csrc/points.cu): same expanded distance and first-minimum rule, no (N, H, W, P) tensor
+                nearest = fused(g, pointsA)
+            else:
+                gg_ = g.reshape(n, fmA.size(1), fmA.size(2), 1, 1, 2)
+                pts = pointsA.reshape(n, 1, 1, num_points, 2, 1)
+                sim = (gg_ @ pts)[..., 0, 0]
+                dist = pts.pow(2).squeeze(-1).sum(dim=-1) + gg_.pow(2).sum(dim=-1).squeeze(-1) - 2 * sim
+                nearest = dist.reshape(n, g.size(1) * g.size(2), num_points).argmin(dim=1)
             congealed = unravel_index(nearest, (g.size(1), g.size(2)))
         if return_full:
             return outA, fmA, congealed
@@ -337,6 +343,31 @@ class ComposedSTN(nn.Module):
         if unnormalize_output_points:
             pointsB = SpatialTransformer.unnormalize(pointsB, imgB.size(-1), imgB.size(-1))
         return (pointsB, congealed_img) if return_congealed_img else pointsB
+
+    def uncongeal_and_splat(self, imgB, points_congealed, colors, sigma, opacity, alpha_channel=None, output_resolution=None,
+                            iters=1, normalize_input_points=False, **stn_forward_kwargs):
+        """`uncongeal_points(imgB, points)` followed by `splat_points(imgB, points, sigma, opacity, colors=...)` (reference
+        applications/propagate_to_images.py:44-78 + utils/vis_tools/helpers.py:134-194, alpha blending) with the grid lookup
+        fused into the first splat's point load (csrc/splat.cu LOOKUP).  -> (propagated images, points (N, P, 2) in pixels)."""
+        assert imgB.size(0) == points_congealed.size(0)
+        if normalize_input_points:
+            points_congealed = SpatialTransformer.normalize(points_congealed, imgB.size(-1), self.stn_in_size)
+        _, gridB = self.forward(imgB, return_warp=True, output_resolution=output_resolution, iters=iters, **stn_forward_kwargs)
+        n, _, h, w = imgB.shape
+        res = imgB.size(-1)
+        sig = torch.full((n,), float(sigma), device=imgB.device) if not torch.is_tensor(sigma) else sigma
+        if alpha_channel is None:
+            alpha_channel = torch.ones(n, points_congealed.size(1), 1, device=imgB.device)
+        fused = getattr(self.ops, "splat2d_lookup", None)
+        blank_img = torch.zeros(n, colors.shape[-1], h, w, device=imgB.device)
+        blank_mask = torch.zeros(n, 1, h, w, device=imgB.device)
+        if fused is not None and imgB.is_cuda and colors.shape[-1] <= 3:
+            prop_obj, pointsB = fused(blank_img, gridB, points_congealed, colors, sig, res, res, False)
+        else:
+            pointsB = SpatialTransformer.unnormalize(self.stns[0]._lookup(gridB, points_congealed), res, res)
+            prop_obj = self.ops.splat2d(blank_img, pointsB, colors, sig, False)
+        prop_mask = self.ops.splat2d(blank_mask, pointsB, alpha_channel, sig, True) * opacity
+        return prop_mask * prop_obj + (1 - prop_mask) * imgB, pointsB
 
     def congeal_points(self, imgA, pointsA, output_resolution=None, iters=1, normalize_input_points=True,
                        unnormalize_output_points=False, return_full=False, **stn_forward_kwargs):

@@ -352,6 +352,25 @@ GG_API int gg_tent_downsample_backward(float* grad_in, const float* grad_out, co
                                        int64_t N, int C, int in_h, int in_w, int stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Point-transfer path, csrc/points.cu + csrc/splat.cu.
+ *   gg_nn_argmin: reference spatial_transformer.py:655-668 (`congeal_points` of a flow STN): index[n, p] = argmin over the
+ *     HW entries of grid (N, HW, 2) of |p|^2 + |g|^2 - 2 g.p (the reference's expanded form and rounding; first minimum
+ *     wins) for points (N, P, 2).  No (N, H, W, P) distance tensor; `workspace` of gg_nn_argmin_workspace(N, P) bytes.
+ *   gg_splat2d_lookup_forward: reference spatial_transformer.py:141-157 (`uncongeal_points`: F.grid_sample of the sampling
+ *     grid at the query points, 'border', align_corners=False; `unnormalize` :621-623) fused into gg_splat2d_forward's point
+ *     load: query (N, P, 2) normalised congealed-frame coordinates, grid (N, grid_h, grid_w, 2); pixel coordinate =
+ *     ((g / unnorm_k) / 2 + 0.5) * unnorm_m with unnorm_k = (res-1)/res, unnorm_m = out_res - 1; points_out (N, P, 2) or NULL
+ *     receives the looked-up coordinates.  C <= 3.
+ * ---------------------------------------------------------------------------------------------- */
+GG_API int64_t gg_nn_argmin_workspace(int64_t N, int64_t P);
+GG_API int gg_nn_argmin(int64_t* index, void* workspace, const float* grid, const float* points, int64_t N, int64_t P, int HW,
+                        void* stream);
+GG_API int gg_splat2d_lookup_forward(float* out, float* points_out, void* workspace, const float* input, const float* grid,
+                                     const float* query, const float* values, const float* sigma, int64_t N, int64_t P,
+                                     int C, int H, int W, int grid_h, int grid_w, float unnorm_k, float unnorm_m,
+                                     int soft_normalize, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training-loop bookkeeping, csrc/optim.cu.
  *   gg_adam_ema_step: reference train.py:126-134 -- torch.optim.Adam.step() for every parameter of both optimisers and the
  *     EMA `accumulate(t_ema, t_module)` (models/__init__.py:19-24) -- as one multi-tensor pass.
@@ -363,7 +382,7 @@ GG_API int gg_tent_downsample_backward(float* grad_in, const float* grad_out, co
  *     reduce_batch=True: out[0] = mean huber|d/dy| + mean huber|d/dx|; backward is gather-form (deterministic).
  * ---------------------------------------------------------------------------------------------- */
 GG_API int gg_adam_ema_step(const void* table, const int* block_tensor, const int* block_chunk, int blocks, int chunk,
-                            float* state, float beta1, float beta2, float eps, float ema_decay, void* stream);
+                            float* state, double beta1, double beta2, double eps, double ema_decay, void* stream);
 GG_API int64_t gg_tv_loss_workspace(int64_t N, int H, int W);
 GG_API int gg_tv_loss_forward(float* out, void* workspace, const float* flow, int64_t N, int H, int W, void* stream);
 GG_API int gg_tv_loss_backward(float* grad_flow, const float* grad_out, const float* flow, int64_t N, int H, int W,

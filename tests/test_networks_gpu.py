@@ -317,3 +317,59 @@ def test_bf16_training_step_tracks_the_fp32_step():
     out = t16.step()
     torch.cuda.synchronize()
     assert all(torch.isfinite(v) for v in out.values())
+
+
+@pytest.mark.parametrize("transforms", [("similarity",), ("similarity", "flow")])
+def test_point_transfer_on_gpu_matches_reference_fixture(transforms):
+    """congeal_points / uncongeal_points / transfer_points on the sm_100a op set (the flow STN's nearest-neighbour search
+    runs in the tiled argmin kernel, csrc/points.cu) against the reference-generated fixture.  The nearest-neighbour indices
+    are integer work: equal to the reference's up to the GPU convolutions' effect on the grid itself (an index may move by
+    one cell where two cells are equidistant to within the float noise of the network)."""
+    from gangealing_b200.stn import get_stn
+    blob = load_golden("points")
+    tag = "pts_" + "_".join(transforms)
+    stn = get_stn(list(transforms), flow_size=64, supersize=64, channel_multiplier=0.25, num_heads=1).eval()
+    opset.fill_parameters(stn, 21, gain=0.3).to(DEV)
+    img_a, img_b, pts = blob[tag + ".img_a"].to(DEV), blob[tag + ".img_b"].to(DEV), blob[tag + ".points"].to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            congealed = stn.congeal_points(img_a, pts)
+            is_index = congealed.dtype != torch.float32
+            ref = blob[tag + ".congealed"]
+            back = stn.uncongeal_points(img_b, ref.to(DEV).float() if is_index else congealed, normalize_input_points=is_index)
+            moved = stn.transfer_points(img_a, img_b, pts)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert congealed.dtype == ref.dtype and congealed.shape == ref.shape
+    if is_index:
+        diff = (congealed.cpu() - ref).abs()
+        assert diff.max() <= 1 and (diff == 0).float().mean() >= 0.8, diff
+    else:
+        assert_close(congealed, ref, rtol=1e-4, what="congealed points")
+    assert_close(back, blob[tag + ".uncongealed"], rtol=2e-4, what="uncongealed points")
+    assert_close(moved, blob[tag + ".transferred"], atol=1.0 if is_index else 1e-2, what="transferred points (pixels)")
+
+
+def test_uncongeal_and_splat_equals_the_two_step_path():
+    """propagate_to_images' per-frame work (uncongeal_points -> splat_points) with the lookup fused into the splat vs the
+    reference's two steps through the same STN."""
+    from gangealing_b200.stn import get_stn
+    from gangealing_b200.splat2d import splat2d
+    from oracle import splat as SP
+    stn = get_stn(["similarity", "flow"], flow_size=64, supersize=128, channel_multiplier=0.25, num_heads=1).eval()
+    opset.fill_parameters(stn, 21, gain=0.2).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    imgs = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).to(DEV)
+    ys, xs = torch.meshgrid(torch.arange(64.), torch.arange(64.), indexing="ij")
+    disc = ((ys - 32) ** 2 + (xs - 32) ** 2) < (0.35 * 64) ** 2
+    pts = torch.stack([xs[disc], ys[disc]], dim=1)[None].repeat(2, 1, 1).to(DEV)
+    colors = torch.randn(2, pts.shape[1], 3, generator=g).to(DEV)
+    with torch.no_grad():
+        fused_img, fused_pts = stn.uncongeal_and_splat(imgs, pts, colors, 1.3, 0.75, output_resolution=128,
+                                                       normalize_input_points=True, padding_mode="border")
+        two_pts = stn.uncongeal_points(imgs, pts, normalize_input_points=True, output_resolution=128, padding_mode="border")
+        two_img = SP.splat_points_ref(imgs, two_pts, 1.3, 0.75, colors, splat_fn=splat2d)
+    assert_close(fused_pts, two_pts, atol=2e-3, what="points")
+    assert_close(fused_img, two_img, rtol=2e-3, what="propagated image")

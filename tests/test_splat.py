@@ -125,3 +125,56 @@ def test_splat2d_argument_checks_and_call_site_contract():
     expect = SP.splat_points_ref(imgs, pts, 0.7, 0.75, colors)
     got = SP.splat_points_ref(imgs.to(DEV), pts.to(DEV), 0.7, 0.75, colors.to(DEV), splat_fn=Splat2D())
     assert_close(got, expect, rtol=2e-4, what="splat_points")
+
+
+# ------------------------------------------------------------------------------------------------ point-transfer kernels
+@pytest.mark.gpu
+def test_nn_argmin_kernel_against_the_reference_formulation():
+    """congeal_points' brute-force search (spatial_transformer.py:655-668): the tiled argmin kernel against the reference's
+    expanded-distance tensor + argmin on the CPU -- EXACT indices wherever the two smallest distances are separated."""
+    from gangealing_b200.splat2d import nn_argmin
+    g = torch.Generator().manual_seed(8)
+    for n, h, w, p in [(2, 16, 16, 37), (1, 128, 128, 3000), (3, 24, 40, 1)]:
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+        grid = torch.stack([xs, ys], -1)[None].repeat(n, 1, 1, 1) + 0.05 * torch.randn(n, h, w, 2, generator=g)
+        pts = torch.rand(n, p, 2, generator=g) * 2 - 1
+        gg_ = grid.reshape(n, h, w, 1, 1, 2)
+        pp = pts.reshape(n, 1, 1, p, 2, 1)
+        sim = (gg_ @ pp)[..., 0, 0]
+        dist = (pp.pow(2).squeeze(-1).sum(dim=-1) + gg_.pow(2).sum(dim=-1).squeeze(-1) - 2 * sim).reshape(n, h * w, p)
+        expect = dist.argmin(dim=1)
+        got = nn_argmin(grid.to(DEV), pts.to(DEV)).cpu()
+        top2 = dist.topk(2, dim=1, largest=False).values
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert decided.float().mean() > 0.99
+        assert torch.equal(got[decided], expect[decided])
+        # wherever the kernel disagrees on an undecided pair it still picked a (numerically) minimal entry
+        picked = dist.gather(1, got[:, None, :]).squeeze(1)
+        assert torch.all(picked <= top2[:, 0] + 1e-5)
+    # exact duplicates: the first index wins, like argmin
+    grid = torch.zeros(1, 4, 4, 2)
+    assert int(nn_argmin(grid.to(DEV), torch.zeros(1, 1, 2, device=DEV))) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sigma", [0.3, 1.3])
+def test_splat2d_lookup_fuses_uncongeal_points_into_the_splat(sigma):
+    """`uncongeal_points` (grid_sample of the sampling grid at the query points + unnormalize, spatial_transformer.py:141-157)
+    fused into the splat's point load: looked-up points and the splatted image against the two-step CPU oracle."""
+    import torch.nn.functional as F
+    from gangealing_b200.splat2d import splat2d_lookup
+    g = torch.Generator().manual_seed(12)
+    n, h, p, res = 2, 64, 5000, 64
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32), indexing="ij")
+    grid = torch.stack([xs, ys], -1)[None].repeat(n, 1, 1, 1) * 0.9 + 0.03 * torch.randn(n, 32, 32, 2, generator=g)
+    query = torch.rand(n, p, 2, generator=g) * 2.2 - 1.1          # some queries beyond the border
+    vals = torch.randn(n, p, 3, generator=g)
+    sig = torch.full((n,), sigma)
+    looked = F.grid_sample(grid.permute(0, 3, 1, 2), query.unsqueeze(2), padding_mode="border", align_corners=False)
+    looked = looked.squeeze(3).permute(0, 2, 1)
+    pts = looked.div((res - 1) / res).div(2).add(0.5).mul(res - 1)            # SpatialTransformer.unnormalize
+    expect = SP.splat2d_ref(torch.zeros(n, 3, h, h), pts, vals, sig, False)
+    out, got_pts = splat2d_lookup(torch.zeros(n, 3, h, h, device=DEV), grid.to(DEV), query.to(DEV), vals.to(DEV), sig.to(DEV),
+                                  res, res, False)
+    assert_close(got_pts, pts, atol=2e-4, what="looked-up points (pixels)")
+    assert_close(out, expect, rtol=2e-3, what="splatted image")
