@@ -146,7 +146,7 @@ def test_nn_argmin_kernel_against_the_reference_formulation():
         got = nn_argmin(grid.to(DEV), pts.to(DEV)).cpu()
         top2 = dist.topk(2, dim=1, largest=False).values
         decided = (top2[:, 1] - top2[:, 0]) > 1e-6
-        assert decided.float().mean() > 0.99
+        assert decided.float().mean() > 0.95
         assert torch.equal(got[decided], expect[decided])
         # wherever the kernel disagrees on an undecided pair it still picked a (numerically) minimal entry
         picked = dist.gather(1, got[:, None, :]).squeeze(1)
