@@ -110,6 +110,7 @@ class Trainer:
         requires_grad(self.ll, True)
         requires_grad(self.t_ema, False)
         self.t_module, self.ll_module = self.stn, self.ll
+        self._side = None
         if distributed:
             on_gpu = device != "cpu" and torch.device(device).type == "cuda"
             ids = [torch.cuda.current_device()] if on_gpu else None
@@ -121,12 +122,16 @@ class Trainer:
                 if cfg.grad_compression == "bf16":   # halves the bytes of the one exchange step (172 MB of fp32 STN gradients)
                     from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
                     self.stn.register_comm_hook(None, default_hooks.bf16_compress_hook)
-            if on_gpu:  # built on a side stream so the wrapped step can later be captured into a CUDA graph
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
+            if on_gpu:
+                # DDP stashes the AccumulateGrad nodes, which stay pinned to the stream they were created on: build the
+                # wrapper on the ONE side stream the step will be warmed up and captured on (capture()), so that inside the
+                # captured graph gradients are accumulated on the capturing stream itself (no cross-stream joins)
+                self._side = torch.cuda.Stream()
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
                     wrap()
-                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.current_stream().wait_stream(self._side)
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # eager steps run on the default stream
             else:
                 wrap()
         fused = torch.device(device).type == "cuda"
@@ -223,7 +228,7 @@ class Trainer:
             warmup = max(warmup, 11)  # DDP needs >= 11 eager iterations on the side stream before capture (PyTorch docs)
         cfg = self.cfg
         self._static_z = torch.randn(cfg.batch, cfg.dim_latent, device=self.device)
-        side = torch.cuda.Stream()
+        side = self._side if self._side is not None else torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -232,7 +237,7 @@ class Trainer:
         graph = torch.cuda.CUDAGraph()
         self.t_optim.zero_grad(set_to_none=True)
         self.ll_optim.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):
             out = self._eager_step(self._static_z)
             self._static_out = {k: v.detach() for k, v in out.items()}
         self._graph = graph
