@@ -49,7 +49,7 @@ SIGNATURES = {
     "gg_blur_nhwc": (_I, [_P] * 12 + [_I, _L] + [_I] * 12 + [_F, _F, _P]),
     "gg_styled_tail_nhwc": (_I, [_P] * 12 + [_I, _I, _F, _F, _L, _I, _L, _P]),
     "gg_styled_tail_backward_workspace": (_L, [_I, _L, _I, _L]),
-    "gg_styled_tail_backward_nhwc": (_I, [_P] * 12 + [_I, _F, _F, _L, _I, _L, _P]),
+    "gg_styled_tail_backward_nhwc": (_I, [_P] * 12 + [_I, _F, _F, _L, _I, _L, _L, _P]),
     "gg_tent_downsample_forward": (_I, [_P] * 4 + [_L, _I, _I, _I, _I, _P]),
     "gg_tent_downsample_backward": (_I, [_P] * 4 + [_L, _I, _I, _I, _I, _P]),
     "gg_feature_distance_workspace": (_L, [_L, _I, _L]),

@@ -360,7 +360,7 @@ int64_t gg_styled_tail_backward_workspace(int dtype, int64_t N, int C, int64_t H
 int gg_styled_tail_backward_nhwc(void* g_raw, float* d_s_next, float* d_demod, float* d_wm, void* workspace,
                                  const void* g_xs, const float* g_rgb, const void* out_saved, const void* raw,
                                  const float* s_next, const float* demod, const float* wm, int dtype, float alpha,
-                                 float scale, int64_t N, int C, int64_t HW, void* stream) {
+                                 float scale, int64_t N, int C, int64_t HW, int64_t reduce_pitch, void* stream) {
   if (N < 0 || C < 0 || HW < 0) return fail(GG_ERR_BAD_ARG, "styled_tail_backward_nhwc: negative size");
   if (dtype != GG_F32 && dtype != GG_BF16) return fail(GG_ERR_UNSUPPORTED, "styled_tail_backward_nhwc: dtype %d not supported", dtype);
   if (N * HW * C == 0) return GG_OK;
@@ -407,14 +407,26 @@ int gg_styled_tail_backward_nhwc(void* g_raw, float* d_s_next, float* d_demod, f
   else styled_tail_bwd_nhwc_kernel<__nv_bfloat16><<<static_cast<unsigned>(grid), kT, smem, st>>>(p);
   GG_CHECK_LAUNCH("styled_tail_backward_nhwc launch");
   if (r > 0) {
-    // partial is [N][K][r*C]: every requested sum is finished straight into its destination (dst[n][i] = sum_k ...)
-    auto finish_row = [&](float* dst, int row, int rows_n) {
-      nhwc_finish_kernel<<<static_cast<unsigned>(N * ((rows_n * C + 31) / 32)), dim3(32, 32), 0, st>>>(
-          dst, static_cast<const float*>(workspace) + static_cast<int64_t>(row) * C, N, K, rows_n * C, r * C);
-    };
-    if (d_s_next) finish_row(d_s_next, p.r_ds, 1);
-    if (d_demod) finish_row(d_demod, p.r_dd, 1);
-    if (d_wm) finish_row(d_wm, p.r_gw, 3);
+    // partial is [N][K][r*C]: ONE finish launch writes every requested sum.  The caller's destinations are slices of one
+    // (N, r, C) block when they are laid out that way (the Python face allocates them so); otherwise one launch per sum.
+    float* first = d_s_next ? d_s_next : (d_demod ? d_demod : d_wm);
+    const bool packed = (!d_s_next || d_s_next == first + static_cast<int64_t>(p.r_ds) * C) &&
+                        (!d_demod || d_demod == first + static_cast<int64_t>(p.r_dd) * C) &&
+                        (!d_wm || d_wm == first + static_cast<int64_t>(p.r_gw) * C) && reduce_pitch == r * C;
+    if (packed) {
+      nhwc_finish_kernel<<<static_cast<unsigned>(N * ((r * C + 31) / 32)), dim3(32, 32), 0, st>>>(
+          first, static_cast<const float*>(workspace), N, K, r * C, r * C);
+    } else {
+      auto finish_row = [&](float* dst, int row, int rows_n) {
+        nhwc_finish_kernel<<<static_cast<unsigned>(N * ((rows_n * C + 31) / 32)), dim3(32, 32), 0, st>>>(
+            dst, static_cast<const float*>(workspace) + static_cast<int64_t>(row) * C, N, K, rows_n * C, r * C);
+      };
+      if (reduce_pitch != C && reduce_pitch != 0 && reduce_pitch != r * C)
+        return fail(GG_ERR_BAD_ARG, "styled_tail_backward_nhwc: reduce_pitch must be C (separate dense outputs) or r*C (packed block)");
+      if (d_s_next) finish_row(d_s_next, p.r_ds, 1);
+      if (d_demod) finish_row(d_demod, p.r_dd, 1);
+      if (d_wm) finish_row(d_wm, p.r_gw, 3);
+    }
     GG_CHECK_LAUNCH("styled_tail_backward_nhwc finish launch");
   }
   return GG_OK;

@@ -157,17 +157,25 @@ def styled_tail_backward(g_xs, g_rgb, out_saved, raw, s_next, demod, wm, want_ds
     want_ds = want_ds and g_xs is not None
     want_dd = want_dd and raw is not None
     want_dwm = want_dwm and g_rgb is not None
-    d_s = torch.empty((n, c), dtype=torch.float32, device=dev) if want_ds else None
-    d_d = torch.empty((n, c), dtype=torch.float32, device=dev) if want_dd else None
-    d_w = torch.empty((n, 3, c), dtype=torch.float32, device=dev) if want_dwm else None
+    # the requested sums are row slices of ONE (N, R, C) block: a single finish launch, views handed to autograd
+    rows = int(want_ds) + int(want_dd) + 3 * int(want_dwm)
+    block = torch.empty((n, rows, c), dtype=torch.float32, device=dev) if rows else None
+    r = 0
+    d_s = d_d = d_w = None
+    if want_ds:
+        d_s = block[:, r]; r += 1
+    if want_dd:
+        d_d = block[:, r]; r += 1
+    if want_dwm:
+        d_w = block[:, r:r + 3]
     code = _lib.dtype_code(out_saved)
     ws = None
-    if want_ds or want_dd or want_dwm:
+    if rows:
         ws = torch.empty(max(1, lib.gg_styled_tail_backward_workspace(code, n, c, h * w) // 4), dtype=torch.float32, device=dev)
     rc = lib.gg_styled_tail_backward_nhwc(g_raw.data_ptr(), _lib.ptr(d_s), _lib.ptr(d_d), _lib.ptr(d_w), _lib.ptr(ws),
                                           _lib.ptr(g_xs), _lib.ptr(g_rgb), out_saved.data_ptr(),
                                           _lib.ptr(raw if want_dd else None),
                                           _lib.ptr(_f32(s_next, n * c)), _lib.ptr(_f32(demod, n * c)), _lib.ptr(_f32(wm, n * 3 * c)),
-                                          code, negative_slope, gain, n, c, h * w, _lib.stream())
+                                          code, negative_slope, gain, n, c, h * w, rows * c, _lib.stream())
     _lib.check(rc, "gg_styled_tail_backward_nhwc")
     return g_raw, d_s, d_d, d_w

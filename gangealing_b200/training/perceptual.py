@@ -62,10 +62,27 @@ class VGG16Slices(nn.Module):
             raise RuntimeError("unexpected VGG16 feature keys (the reference slices stop at relu5_3): %s" % unexpected[:4])
         return self.load_state_dict({own[k]: v for k, v in state_dict.items() if k in own}, strict=strict)
 
-    def forward(self, x):
+    def forward(self, x, ops=None):
+        """ops: the sm_100a op set -> every Conv2d + ReLU pair runs as a bias-free cuDNN convolution followed by ONE
+        hand-written bias+ReLU pass (`fused_leaky_relu(x, bias, negative_slope=0, scale=1)` = relu(x + b), the channels-last
+        streaming kernel of csrc/nhwc.cu) instead of cuDNN's separate broadcast bias-add kernel + ATen's clamp (two passes
+        over the feature map; 1.2 ms of a 25 ms bf16 step, profiles/r02_step_b32_bf16_launches_v1.txt).  None: plain modules."""
         outs = []
         for s in self.slices():
-            x = s(x)
+            if ops is None or not x.is_cuda:
+                x = s(x)
+            else:
+                layers = list(s.children())
+                i = 0
+                while i < len(layers):
+                    m = layers[i]
+                    if isinstance(m, nn.Conv2d) and i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU):
+                        x = nn.functional.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+                        x = ops.fused_leaky_relu(x, m.bias.float() if m.bias.dtype != torch.float32 else m.bias, 0.0, 1.0)
+                        i += 2
+                    else:
+                        x = m(x)
+                        i += 1
             outs.append(x)
         return outs
 
@@ -125,12 +142,13 @@ class PerceptualLoss(nn.Module):
         # every convolution (22% of the step in profiles/r01_step_launches_b8_summary.txt)
         cl = torch.channels_last if in0.is_cuda else torch.contiguous_format
         dt = self.net.slice1[0].weight.dtype   # bf16 when the Trainer runs BASELINE config 3
-        f0 = self.net(self.scaling_layer(in0).to(dt).contiguous(memory_format=cl))
-        f1 = self.net(self.scaling_layer(in1).to(dt).contiguous(memory_format=cl))
         ops = self.ops
         if ops is None:
             from ..opset import cuda_ops
             ops = cuda_ops()
+        native = ops if getattr(ops, "name", None) == "sm_100a" else None
+        f0 = self.net(self.scaling_layer(in0).to(dt).contiguous(memory_format=cl), native)
+        f1 = self.net(self.scaling_layer(in1).to(dt).contiguous(memory_format=cl), native)
         val = 0
         for k, (a, b) in enumerate(zip(f0, f1)):
             # normalise, difference, (weights,) channel sum and spatial mean in one pass over both maps (csrc/lpips.cu)

@@ -102,7 +102,11 @@ class Trainer:
                                         dim_latent=cfg.dim_latent).to(device)
         self.loss_fn = get_perceptual_loss(device, seed=cfg.seed + 1, ops=ops)
         if act_dtype != torch.float32:
-            self.loss_fn.net.to(act_dtype)     # frozen VGG16: bf16 weights and feature maps, fp32 distance
+            # frozen VGG16: bf16 filters and feature maps; biases stay fp32 (applied by the fused bias+ReLU kernel, which
+            # takes fp32 per-channel constants); fp32 distance
+            for m in self.loss_fn.net.modules():
+                if isinstance(m, nn.Conv2d):
+                    m.weight.data = m.weight.data.to(act_dtype)
         self.resize_fake2stn = (BilinearDownsample(cfg.gen_size // cfg.flow_size, 3, ops=ops).to(device)
                                 if cfg.gen_size > cfg.flow_size else nn.Sequential())
         requires_grad(self.generator, False)

@@ -298,6 +298,9 @@ GG_API int gg_blur_nhwc(void* out, void* out2, const void* in, const float* kern
  *        d_s_next[n,c] = sum_p g_xs*out;  d_demod[n,c] = sum_p g_t*raw;  d_wm[n,o3,c] = sum_p g_rgb[n,o3,p]*out
  *      (each NULL: skipped; g_xs or g_rgb may be NULL; demod NULL: g_raw = g_t -- the blur layers apply demod in
  *      gg_blur_nhwc mode 2).  `workspace`: gg_styled_tail_backward_workspace() bytes.  Deterministic reductions.
+ *      reduce_pitch: floats between consecutive samples of the sum outputs -- C (each a dense (N, C) / (N, 3, C) tensor) or
+ *      R*C when they are the row slices [d_s_next | d_demod | d_wm x3] (requested ones only, in that order) of ONE (N, R, C)
+ *      block, which is then finished by a single launch.
  * ---------------------------------------------------------------------------------------------- */
 GG_API int gg_styled_tail_nhwc(void* out, void* xs, float* rgb, const void* raw, const float* noise,
                                const float* noise_weight, const float* bias, const float* demod, const float* s_next,
@@ -307,7 +310,8 @@ GG_API int64_t gg_styled_tail_backward_workspace(int dtype, int64_t N, int C, in
 GG_API int gg_styled_tail_backward_nhwc(void* g_raw, float* d_s_next, float* d_demod, float* d_wm, void* workspace,
                                         const void* g_xs, const float* g_rgb, const void* out_saved, const void* raw,
                                         const float* s_next, const float* demod, const float* wm, int dtype,
-                                        float alpha, float scale, int64_t N, int C, int64_t HW, void* stream);
+                                        float alpha, float scale, int64_t N, int C, int64_t HW, int64_t reduce_pitch,
+                                        void* stream);
 
 /* to-RGB on channels-last activations (reference models/stylegan2/networks.py:389-405 `ToRGB.forward`: a 1x1 modulated
  * convolution without demodulation + bias + the up-sampled skip image; the reference builds B filter banks and runs a

@@ -90,7 +90,7 @@ def test_argument_validation_of_the_channels_last_and_loss_entry_points():
     assert dll.gg_styled_tail_nhwc(None, one, None, one, *st, 0, 3, 0.2, 1.0, 1, 32, 16, None) == -1     # xs without s_next
     assert dll.gg_styled_tail_nhwc(one, None, None, one, *st, 0, 2, 0.2, 1.0, 1, 32, 16, None) == -2     # act
     assert dll.gg_styled_tail_backward_nhwc(one, None, None, None, None, None, None, one, None, None, None, None,
-                                            0, 0.2, 1.0, 1, 32, 16, None) == -1                          # no upstream gradient
+                                            0, 0.2, 1.0, 1, 32, 16, 32, None) == -1                      # no upstream gradient
     assert dll.gg_styled_tail_backward_nhwc(one, None, None, None, None, one, None, one, None, None, None, None,
-                                            0, 0.2, 1.0, 1, 32, 16, None) == -1                          # g_xs without s_next
+                                            0, 0.2, 1.0, 1, 32, 16, 32, None) == -1                      # g_xs without s_next
     assert dll.gg_styled_tail_backward_workspace(0, 2, 64, 256) > 0
