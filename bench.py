@@ -112,7 +112,14 @@ def cpu_threads():
 
 
 def cpu_step_rate(batch, steps=1, warmup=0):
-    """The reference algorithm (oracle port: same host code, CPU op set) on all host cores -> images/s."""
+    """The reference's training iteration on all host cores -> (images/s, s/step, kind).  kind "reference": the UNMODIFIED
+    reference code (oracle/_ref/refpy_cpu, byte-compiled from /root/reference by oracle/build_ref.py) through its own native
+    CPU branches (oracle/reference_step.py); kind "port": the oracle port (this repo's host code on the oracle's CPU op
+    set) when that tree was not built."""
+    from oracle import reference_step
+    if reference_step.available() and os.environ.get("GG_CPU_KIND", "reference") == "reference":
+        rate, sec, _ = reference_step.step_rate(batch, steps=steps, warmup=warmup, threads=cpu_threads())
+        return rate, sec, "reference"
     from oracle import opset
     from gangealing_b200.training import TrainConfig, Trainer
     torch.set_num_threads(cpu_threads())
@@ -125,7 +132,7 @@ def cpu_step_rate(batch, steps=1, warmup=0):
         out = tr.step()
     float(out["p"].detach())
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return batch * steps / dt, dt / steps, "port"
 
 
 def run_reference(args):
@@ -139,10 +146,11 @@ def run_reference(args):
     max_steps = int(os.environ.get("GG_CPU_MAX_STEPS", "6"))
     steps = max(1, min(args.steps, max_steps))
     warm = max(0, min(args.warmup, 1))
-    rate, sec = cpu_step_rate(args.cpu_batch, steps=steps, warmup=warm)
+    rate, sec, kind = cpu_step_rate(args.cpu_batch, steps=steps, warmup=warm)
     sample = "%d step(s) of per-step batch %d (a bounded sample of the %d-per-GPU workload), %d host threads" % (
         steps, args.cpu_batch, args.batch, cores)
-    cfg = {"workload": WORKLOAD + " -- BASELINE config 2 (fp32)", "step_mode": "eager, CPU (reference algorithm, oracle port)",
+    cfg = {"workload": WORKLOAD + " -- BASELINE config 2 (fp32)", "step_mode": ("eager, CPU: the unmodified reference code (train.py:106-136 over oracle/_ref/refpy_cpu)" if kind == "reference"
+                         else "eager, CPU (reference algorithm, oracle port)"),
            "per_step_batch": args.cpu_batch, "gen_size": 256, "flow_size": 128, "parallelism": "none (rank 0 host cores)",
            "activation_layout": "NCHW", "host_threads": cores,
            "steps_requested": args.steps, "warmup_requested": args.warmup,
@@ -150,7 +158,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -322,8 +330,8 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            rate, sec = cpu_step_rate(args.cpu_batch, steps=1, warmup=0)
-            cpu = {"value": rate, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+            rate, sec, kind = cpu_step_rate(args.cpu_batch, steps=1, warmup=0)
+            cpu = {"value": rate, "unit": UNIT, "cores": cpu_threads(), "kind": kind,
                    "sample": "1 step of per-step batch %d on %d host threads of %d cores (%.1f s)" % (
                        args.cpu_batch, cpu_threads(), os.cpu_count(), sec)}
         except Exception as exc:  # the baseline must never take the bench down

@@ -18,6 +18,9 @@ for sm_100a ("the kernel bar").  No reference source is c
                                     unchanged" claim of SURVEY.md 8(b)).  models/stylegan2/op is NOT compiled (it is
                                     the kernel boundary and JIT-builds CUDA at import); antialiased_sampling.py is
                                     compiled only so that tools/opbench.py --stn can time the reference's MipmapWarp.
+  refpy_cpu/                      : the same byte-compiled tree WITH models/stylegan2/op: the complete reference
+                                    network code for the host-CPU arm of bench.py (oracle/reference_step.py stubs the
+                                    import-time JIT build, the reference then takes its own native CPU branches).
 """
 import os
 import shutil
@@ -69,28 +72,42 @@ _REFPY_SKIP = (os.path.join("models", "stylegan2", "op"),)
 _REFPY_UTILS = ("__init__.py", "distributed.py", "download.py", "annealing.py")
 
 
-def build_refpy():
-    """Byte-compile the reference's network code into oracle/_ref/refpy (sourceless .pyc tree)."""
+# A second, COMPLETE tree (models/stylegan2/op included) for the CPU arm of bench.py: with torch.utils.cpp_extension.load
+# stubbed, the reference's ops take their own native CPU branches (op/upfirdn2d.py:146-149, op/fused_act.py:87-94), so
+# `bench.py --impl reference` times the UNMODIFIED reference algorithm on the host cores (oracle/reference_step.py).
+REFPY_CPU = os.path.join(OUT, "refpy_cpu")
+
+
+def build_refpy(root=None, skip=None):
+    """Byte-compile the reference's network code into oracle/_ref/refpy (sourceless .pyc tree); with `root`/`skip`
+    given, into another tree (refpy_cpu: nothing skipped)."""
     import py_compile
+    if root is None:
+        build_refpy(REFPY_CPU, ())
+        root, skip = REFPY, _REFPY_SKIP
     todo = []
     for base, _, files in os.walk(os.path.join(REF, "models")):
         for f in files:
             if f.endswith(".py"):
                 rel = os.path.relpath(os.path.join(base, f), REF)
-                if not any(rel.startswith(s) for s in _REFPY_SKIP):
+                if not any(rel.startswith(s) for s in skip):
                     todo.append(rel)
     todo += [os.path.join("utils", f) for f in _REFPY_UTILS if os.path.exists(os.path.join(REF, "utils", f))]
     for rel in todo:
-        dst = os.path.join(REFPY, rel + "c")
+        dst = os.path.join(root, rel + "c")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile: tracebacks name the reference file, not a path inside this repo
         py_compile.compile(os.path.join(REF, rel), cfile=dst, dfile=os.path.join("<reference>", rel), doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
-    return REFPY
+    return root
 
 
 def refpy_available():
     return os.path.exists(os.path.join(REFPY, "models", "__init__.pyc"))
+
+
+def refpy_cpu_available():
+    return os.path.exists(os.path.join(REFPY_CPU, "models", "stylegan2", "op", "__init__.pyc"))
 
 
 def load_ref(name):

@@ -1,15 +1,22 @@
-"""The bench line contract, checked on the one arm that runs without a GPU: `bench.py --impl reference` (the CPU port of
-the step on the host cores, a bounded sample).  Keys and invariants are the ones the driver reads."""
+"""The bench line contract, checked on the one arm that runs without a GPU: `bench.py --impl reference` (the reference's
+step on the host cores, a bounded sample: the unmodified reference code when oracle/_ref/refpy_cpu is built, else the
+oracle port).  Keys and invariants are the ones the driver reads."""
 import json
 import os
 import subprocess
 import sys
 
+import pytest
+
 from conftest import ROOT
+from oracle import reference_step
 
 
-def test_reference_arm_prints_one_contract_line():
-    env = dict(os.environ)
+@pytest.mark.parametrize("kind", ["reference", "port"])
+def test_reference_arm_prints_one_contract_line(kind):
+    if kind == "reference" and not reference_step.available():
+        pytest.skip("oracle/_ref/refpy_cpu not built (python -m oracle.build_ref)")
+    env = dict(os.environ, GG_CPU_KIND=kind)
     proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
                            "--warmup", "0", "--cpu-batch", "1"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert proc.returncode == 0, proc.stderr[-2000:]
@@ -24,7 +31,7 @@ def test_reference_arm_prints_one_contract_line():
     assert line["vs_baseline"] is None and line["dtype"] == "f32" and line["data"] == "synthetic"
     assert isinstance(line["config"], dict) and "workload" in line["config"] and "model" not in line["config"]
     cpu = line["cpu_baseline"]
-    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and cpu["sample"]
+    assert cpu["kind"] == kind and cpu["cores"] >= 1 and cpu["value"] == line["value"] and cpu["sample"]
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["unit"] == line["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
