@@ -16,6 +16,7 @@
 //    Algorithmic bytes/launch = s*M*(Hin*Win + Hout*Wout) [+ s*N*Hout*Wout noise + 4*(C+1+16)].
 //  * upfirdn2d_generic_kernel: any up/down/pad/filter size (RGB skip up x2, its backward down x2,
 //    5x5 test filters ...): one thread per output, polyphase tap walk, fp32 accumulate.
+#include <algorithm>
 #include <utility>
 
 #include "common.cuh"
@@ -105,6 +106,89 @@ upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ in, const fl
       acc = t * ((ep.act == 3 && t < 0.f) ? ep.alpha * ep.scale : ep.scale);
     }
     out[idx] = Cvt<T>::from_f(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// polyphase x2 resamplers (4x4 taps, fp32): the to-RGB skip's `Upsample` (up 2, pad (2,1): networks.py:28-46) and its
+// backward (down 2, pad (1,1): upfirdn2d.py:111-116).  Of the 16 taps only a 2x2 phase touches a non-zero sample of the
+// zero-inserted signal, so the up-sampler does 4 FMAs per output; a thread owns 2 input columns x 1 input row ->
+// 2 rows x 4 columns of output (two 16-byte stores); the decimator owns 2 adjacent outputs (one 16-byte + 2 scalar
+// loads per input row, one 8-byte store).  HBM-bound: 4*M*(5*H*W) bytes; neighbours are L1/L2 hits.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+up2_k4_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ taps, int64_t planes,
+              int H, int W) {
+  float f[4][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i >> 2][i & 3] = __ldg(taps + i);
+  const int wp = W >> 1;
+  const int64_t total = planes * H * wp;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(idx % wp);
+    const int64_t q = idx / wp;
+    const int j = static_cast<int>(q % H);
+    const int64_t m = q / H;
+    const float* p = in + (m * H + j) * static_cast<int64_t>(W) + 2 * t;
+    float v[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = j - 1 + r;
+      const bool ok = iy >= 0 && iy < H;
+      const float* row = p + (r - 1) * W;
+      const float2 c = ok ? __ldg(reinterpret_cast<const float2*>(row)) : make_float2(0.f, 0.f);
+      v[r][1] = c.x;
+      v[r][2] = c.y;
+      v[r][0] = (ok && t > 0) ? __ldg(row - 1) : 0.f;
+      v[r][3] = (ok && 2 * t + 2 < W) ? __ldg(row + 2) : 0.f;
+    }
+    float* o = out + ((m * 2 * H + 2 * j) * static_cast<int64_t>(2 * W)) + 4 * t;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {        // output row 2j+a: input rows j-1+a+d' with tap row 3-a-2d'
+      float r4[4];
+#pragma unroll
+      for (int ox = 0; ox < 4; ++ox) {   // output col 4t+ox: phase b = ox&1, first input col index (ox+1)>>1
+        const int b = ox & 1, c0 = (ox + 1) >> 1;
+        float acc = v[a][c0] * f[3 - a][3 - b];
+        acc = fmaf(v[a][c0 + 1], f[3 - a][1 - b], acc);
+        acc = fmaf(v[a + 1][c0], f[1 - a][3 - b], acc);
+        acc = fmaf(v[a + 1][c0 + 1], f[1 - a][1 - b], acc);
+        r4[ox] = acc;
+      }
+      __stcs(reinterpret_cast<float4*>(o + a * 2 * W), make_float4(r4[0], r4[1], r4[2], r4[3]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+down2_k4_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ taps, int64_t planes,
+                int Hi, int Wi) {
+  float f[4][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i >> 2][i & 3] = __ldg(taps + i);
+  const int Ho = Hi >> 1, Wo = Wi >> 1, wp = Wo >> 1;
+  const int64_t total = planes * Ho * wp;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(idx % wp);
+    const int64_t q = idx / wp;
+    const int oy = static_cast<int>(q % Ho);
+    const int64_t m = q / Ho;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {     // input row 2oy-1+ky, tap row 3-ky; cols 4t-1 .. 4t+4
+      const int iy = 2 * oy - 1 + ky;
+      if (iy < 0 || iy >= Hi) continue;
+      const float* row = in + (m * Hi + iy) * static_cast<int64_t>(Wi) + 4 * t;
+      const float4 c = __ldg(reinterpret_cast<const float4*>(row));
+      const float l = t > 0 ? __ldg(row - 1) : 0.f;
+      const float r = 4 * t + 4 < Wi ? __ldg(row + 4) : 0.f;
+      const float* fr = f[3 - ky];
+      o0 = fmaf(l, fr[3], fmaf(c.x, fr[2], fmaf(c.y, fr[1], fmaf(c.z, fr[0], o0))));
+      o1 = fmaf(c.y, fr[3], fmaf(c.z, fr[2], fmaf(c.w, fr[1], fmaf(r, fr[0], o1))));
+    }
+    *reinterpret_cast<float2*>(out + (m * Ho + oy) * static_cast<int64_t>(Wo) + 2 * t) = make_float2(o0, o1);
   }
 }
 
@@ -801,6 +885,27 @@ int gg_upfirdn2d(void* out, const void* in, const float* kernel, int dtype, int6
     if (plan_band(dtype, major, in_h, in_w, out_h, out_w, pad_x0, pad_y0, out, nullptr, &pl))
       return launch_band<false>(dtype, pl, out, in, kernel, kernel_h, kernel_w, nullptr, nullptr, nullptr,
                                 nullptr, st);
+  }
+  // polyphase fast paths of the to-RGB skip (fp32 planes, 4x4 taps): x2 up with pad (2,1), x2 down with pad (1,1)
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0;
+  if (dtype == GG_F32 && kernel_h == 4 && kernel_w == 4 && aligned16 && in_h > 0 && in_w > 0) {
+    const int cap = sm_count() * 16;
+    if (up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1 && pad_x0 == 2 && pad_y0 == 2 && pad_x1 == 1 && pad_y1 == 1 &&
+        (in_w & 1) == 0) {
+      const int64_t work = major * in_h * (in_w >> 1);
+      const int grid = static_cast<int>(std::min<int64_t>((work + 255) / 256, cap));
+      up2_k4_kernel<<<grid, 256, 0, st>>>(static_cast<float*>(out), static_cast<const float*>(in), kernel, major, in_h, in_w);
+      GG_CHECK_LAUNCH("upfirdn2d x2 up-sampler launch");
+      return GG_OK;
+    }
+    if (up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2 && pad_x0 == 1 && pad_y0 == 1 && pad_x1 == 1 && pad_y1 == 1 &&
+        (in_w & 3) == 0 && (in_h & 1) == 0) {
+      const int64_t work = major * (in_h >> 1) * (in_w >> 2);
+      const int grid = static_cast<int>(std::min<int64_t>((work + 255) / 256, cap));
+      down2_k4_kernel<<<grid, 256, 0, st>>>(static_cast<float*>(out), static_cast<const float*>(in), kernel, major, in_h, in_w);
+      GG_CHECK_LAUNCH("upfirdn2d x2 decimator launch");
+      return GG_OK;
+    }
   }
   GenericParams gp{in_h, in_w, out_h, out_w, kernel_h, kernel_w, up_x, up_y, down_x, down_y, pad_x0, pad_y0};
   const int64_t total = major * out_h * static_cast<int64_t>(out_w);

@@ -336,6 +336,28 @@ warp_fwd_kernel(T* __restrict__ out, float* __restrict__ levels_out, const T* __
   }
 }
 
+// ---------------------------------------------------------------- integer work of the sampler, exported for exact tests
+// One int4 per output pixel: (x0, y0) = the north-west bilinear corner in source pixels after the padding-mode transform
+// (ATen grid_sampler's floor(ix), floor(iy)), and (l0, l1) = floor / ceil of the level of detail -- produced by the SAME
+// device functions (sample_geom, level_of_detail) the sampling kernels call, so the parity tests can compare the integers
+// themselves with the oracle's (oracle/sampling.py grid_sample_bilinear / mipmap_warp_ref) instead of inferring them.
+__global__ void __launch_bounds__(256)
+sample_indices_kernel(int4* __restrict__ out, const float* __restrict__ grid, const __grid_constant__ WarpParams p, int64_t total) {
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % p.wo);
+    const int64_t t = idx / p.wo;
+    const int oy = static_cast<int>(t % p.ho);
+    const int64_t n = t / p.ho;
+    const float* grid_n = grid + n * p.ho * static_cast<int64_t>(p.wo) * 2;
+    const float2 g = *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(oy) * p.wo + ox) * 2);
+    const SampleGeom s = sample_geom(g.x, g.y, p.hs, p.ws, p.pad_mode);
+    auto grid_at = [&](int y, int x) { return *reinterpret_cast<const float2*>(grid_n + (static_cast<int64_t>(y) * p.wo + x) * 2); };
+    const LevelInfo li = level_of_detail(grid_at, oy, ox, p.ho, p.wo, p.hs, p.ws, p.max_level, p.min_level);
+    out[idx] = make_int4(s.x0, s.y0, li.l0, li.l1);
+  }
+}
+
 // ---------------------------------------------------------------- the STN's sampling in ONE pass
 // north_star: "the STN's antialiased bilinear grid_sample fused with flow-compose in one pass".  The sampling grid is never
 // read from memory: every output pixel GENERATES its coordinate (and those of its 4 neighbours, for the level of detail)
@@ -725,6 +747,21 @@ int gg_mipmap_build_backward(float* grad_src, float* grad_pyramid, int64_t plane
                                                                        py.hs, py.ws, py.lp, total);
     GG_CHECK_LAUNCH("mip_down_bwd launch");
   }
+  return GG_OK;
+}
+
+int gg_warp_sample_indices(int32_t* indices, const float* grid, int64_t N, int hs, int ws, int ho, int wo,
+                           float max_level, float min_level, int padding_mode, void* stream) {
+  WarpParams wp;
+  int rc = fill_params(&wp, N, 1, hs, ws, ho, wo, padding_mode, 0, max_level, min_level);
+  if (rc != GG_OK) return rc;
+  const int64_t total = N * ho * static_cast<int64_t>(wo);
+  if (total == 0) return GG_OK;
+  if (!indices || !grid) return fail(GG_ERR_BAD_ARG, "warp_sample_indices: null tensor");
+  if (reinterpret_cast<uintptr_t>(indices) & 15) return fail(GG_ERR_BAD_ARG, "warp_sample_indices: indices must be 16-byte aligned");
+  sample_indices_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<int4*>(indices), grid, wp, total);
+  GG_CHECK_LAUNCH("sample_indices launch");
   return GG_OK;
 }
 

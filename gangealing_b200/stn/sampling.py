@@ -250,6 +250,26 @@ def stn_sample_flow(inputs, low, mask, identity_flow, base_warp, alpha, downsamp
     return out, grid, delta, (levels if extra > 0 else None)
 
 
+def sample_indices(grid, source_hw, max_num_levels=8, min_level=0.0, padding_mode="border"):
+    """The sampler's integer work for `grid` (N, Ho, Wo, 2) over a source of size `source_hw`: int32 (N, Ho, Wo, 4) =
+    (x0, y0, l0, l1) -- north-west bilinear corner after the padding-mode transform and floor / ceil of the level of
+    detail, from the device functions the sampling kernels use (gg_warp_sample_indices; for exact parity tests)."""
+    _lib.require_cuda(grid)
+    hs, ws = int(source_hw[0]), int(source_hw[1])
+    max_level = float(max_num_levels) - 1.0
+    wanted = int(math.ceil(max(max_level, float(min_level), 0.0)))
+    extra = feasible_levels(hs, ws, wanted)
+    if extra < wanted:
+        max_level, min_level = min(max_level, float(extra)), min(float(min_level), float(extra))
+    g = grid.detach().float().contiguous()
+    n, ho, wo, _ = g.shape
+    out = torch.empty(n, ho, wo, 4, dtype=torch.int32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.load().gg_warp_sample_indices(_lib.ptr(out), _lib.ptr(g), n, hs, ws, ho, wo, max_level, float(min_level),
+                                                     _pad_code(padding_mode), _lib.stream()), "warp_sample_indices")
+    return out
+
+
 def _pad_code(padding_mode):
     try:
         return _lib.PAD_MODES[padding_mode]

@@ -170,6 +170,12 @@ GG_API int gg_mipmap_warp_backward(float* grad_src, float* grad_pyramid, float* 
                                    const float* grid, int dtype, int64_t N, int C, int hs, int ws, int ho,
                                    int wo, int extra_levels, float max_level, float min_level,
                                    int padding_mode, void* stream);
+/* The sampler's INTEGER work, exported for exact parity tests (no reference counterpart: ATen's grid_sampler_2d and
+ * antialiased_sampling.py:228-229 compute these integers internally).  indices: int32 (N, Ho, Wo, 4), 16-byte aligned =
+ * (x0, y0, l0, l1): north-west bilinear corner after the padding-mode transform, floor / ceil of the level of detail --
+ * evaluated by the same device functions as gg_mipmap_warp_forward / gg_stn_sample_forward. */
+GG_API int gg_warp_sample_indices(int32_t* indices, const float* grid, int64_t N, int hs, int ws, int ho, int wo,
+                                  float max_level, float min_level, int padding_mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Flow composition of the flow STN head -- replaces upsample_flow + identity add + apply_affine + alpha lerp

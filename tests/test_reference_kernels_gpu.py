@@ -76,6 +76,21 @@ def test_upfirdn2d_generic_filter_equals_the_reference_cuda_kernel(ref_upfirdn2d
     assert_close(op.upfirdn2d(x.contiguous(memory_format=CL), k, pad=(2, 1)), expect, rtol=1e-5, what="NHWC")
 
 
+@pytest.mark.parametrize("shape,up,down,pad", [((2, 3, 64, 64), 2, 1, (2, 1)), ((3, 3, 4, 4), 2, 1, (2, 1)), ((1, 3, 6, 10), 2, 1, (2, 1)),
+                                               ((2, 3, 128, 128), 1, 2, (1, 1)), ((3, 3, 8, 8), 1, 2, (1, 1)), ((1, 2, 12, 20), 1, 2, (1, 1)),
+                                               ((1, 3, 7, 9), 2, 1, (2, 1)), ((1, 3, 10, 10), 1, 2, (1, 1))])   # last two: generic path
+def test_upfirdn2d_x2_resamplers_with_an_asymmetric_filter(ref_upfirdn2d, shape, up, down, pad):
+    """The polyphase x2 up-sampler / decimator (to-RGB skip and its backward) with a NON-symmetric 4x4 filter: tap flipping
+    and phase selection must follow the reference kernel (upfirdn2d_kernel.cu:137), exactly as the generic path does."""
+    from gangealing_b200 import op
+    g = torch.Generator().manual_seed(shape[2] * 7 + up)
+    x = torch.randn(*shape, generator=g).to(DEV)
+    k = torch.randn(4, 4, generator=g).to(DEV)
+    expect = ref_upfirdn2d(x, k, up, down, pad)
+    assert_close(op.upfirdn2d(x, k, up=up, down=down, pad=pad), expect, rtol=1e-5, what="kernel vs reference CUDA")
+    assert_close(so.upfirdn2d_ref(x.cpu(), k.cpu(), up=up, down=down, pad=pad), expect, rtol=1e-5, what="CPU oracle")
+
+
 @pytest.mark.parametrize("shape", [(2, 128, 256, 256), (4, 512, 64, 64), (3, 512), (2, 64, 33, 31)])
 def test_fused_bias_act_forward_and_backward_equal_the_reference_cuda_kernel(ref_fused, shape):
     from gangealing_b200 import op

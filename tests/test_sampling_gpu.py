@@ -136,3 +136,46 @@ def test_bilinear_downsample_errors():
         stn.BilinearDownsample(4, 3).to(DEV)(torch.zeros(1, 3, 2, 2, device=DEV))   # plane not larger than stride/2
     y = stn.BilinearDownsample(2, 3).to(DEV)(torch.zeros(0, 3, 8, 8, device=DEV))
     assert y.shape == (0, 3, 4, 4)
+
+
+@pytest.mark.parametrize("mode", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("hs,ws", [(128, 128), (64, 256)])
+def test_sampler_integer_work_is_bit_exact(mode, hs, ws):
+    """The sampler's INTEGER work compared as integers (north_star: "bit-exact for sampling-grid integer/index work"):
+    bilinear corner indices (x0, y0) after the padding-mode transform and the floor / ceil level indices, exported by
+    gg_warp_sample_indices from the device functions the sampling kernels call, vs the oracle's
+    (oracle/sampling.py grid_sample_bilinear / mipmap_levels = ATen grid_sampler + antialiased_sampling.py:197-229).
+
+    (a) DYADIC grid: every coordinate k/512 -- all of ((g+1)*size-1)/2, the reflection fold and the floor are exact in
+        fp32 on both sides (no rounding, so FMA contraction cannot matter): ALL pixels must agree, including the exact
+        ties where the source coordinate IS an integer and the far out-of-range coordinates of every padding mode.
+    (b) random smooth grid: exact wherever the oracle's coordinate is not within 1e-4 px of an integer (there the last
+        ulp of the fp32 evaluation order decides, on the GPU as in ATen's own CUDA kernel); that exempt set must be tiny."""
+    from gangealing_b200.stn import sampling as GS
+    g = torch.Generator().manual_seed(hs + ws)
+    n, ho, wo = 2, 96, 80
+    k = torch.randint(-900, 900, (n, ho, wo, 2), generator=g)
+    k[0, :8, :8] = torch.tensor([4, -4])                 # exact ties: coordinate lands on an integer pixel
+    k[0, 8:16, :8] = torch.tensor([-512, 512])           # the two borders of the normalised range
+    dyadic = k.float() / 512.0
+    theta = torch.tensor([[[0.9, 0.2, 0.05], [-0.15, 1.3, -0.1]], [[2.2, 0.0, 0.3], [0.1, 1.9, 0.0]]])
+    smooth = F.affine_grid(theta, (n, 1, ho, wo), align_corners=False) + 0.03 * torch.randn(n, ho, wo, 2, generator=g)
+    img = torch.zeros(n, 1, hs, ws)
+    for name, grid in (("dyadic", dyadic), ("smooth", smooth)):
+        got = GS.sample_indices(grid.to(DEV), (hs, ws), 3.5, 0.0, mode).cpu()
+        _, (x0, y0) = S.grid_sample_bilinear(img, grid, mode)
+        lv = S.mipmap_levels(grid, hs, ws, 3.5)
+        ix = S.source_index(grid[..., 0], ws, mode)
+        iy = S.source_index(grid[..., 1], hs, mode)
+        if name == "dyadic":
+            corner_ok = torch.ones_like(x0, dtype=torch.bool)
+        else:
+            corner_ok = ((ix - ix.round()).abs() > 1e-4) & ((iy - iy.round()).abs() > 1e-4)
+            assert corner_ok.float().mean() > 0.995
+        assert torch.equal(got[..., 0][corner_ok].long(), x0[corner_ok]), name + " x0"
+        assert torch.equal(got[..., 1][corner_ok].long(), y0[corner_ok]), name + " y0"
+        level_ok = (lv - lv.round()).abs() > 1e-5
+        level_ok |= lv == 0                                 # the clamp: distance <= 1 px is level 0 exactly on both sides
+        assert level_ok.float().mean() > 0.995
+        assert torch.equal(got[..., 2][level_ok].long(), lv.floor().long()[level_ok]), name + " floor(level)"
+        assert torch.equal(got[..., 3][level_ok].long(), lv.ceil().long()[level_ok]), name + " ceil(level)"

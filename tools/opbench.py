@@ -22,12 +22,30 @@ def peak_gbs():
     return 6650.0, "fallback"
 
 
+GRAPH = False   # --graph: time a captured CUDA graph of `iters` calls (device time only; no Python / launch overhead)
+
+
 def timeit(fn, pools, iters=20, warmup=3):
-    """fn(i) runs on input set i (rotating) -> ms per call (mean over iters)."""
+    """fn(i) runs on input set i (rotating) -> ms per call (mean over iters).  With --graph the `iters` calls are captured
+    into ONE CUDA graph and the replay is timed: what a kernel costs inside the captured training step (both this repo's
+    ops and the reference's pybind kernels launch on the current stream, so both capture)."""
     for i in range(warmup):
         fn(i % pools)
     torch.cuda.synchronize()
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if GRAPH:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(iters):
+                fn(i % pools)
+        graph.replay()
+        torch.cuda.synchronize()
+        st.record()
+        graph.replay()
+        en.record()
+        torch.cuda.synchronize()
+        del graph
+        return st.elapsed_time(en) / iters
     st.record()
     for i in range(iters):
         fn(i % pools)
@@ -187,6 +205,7 @@ def reference_bar(B, dev, k4, timeit, pool_count, peak, json_path):
     if json_path:
         os.makedirs(os.path.dirname(os.path.abspath(json_path)), exist_ok=True)
         json.dump({"batch": B, "dtype": "float32", "peak_gbs": peak,
+                   "timing": "CUDA graph replay of 20 calls (device time)" if GRAPH else "eager calls (includes launch overhead)",
                    "what": "reference CUDA kernels (recompiled sm_100a) vs this repo, same inputs, CUDA events, >L2 input pools",
                    "rows": rows}, open(json_path, "w"), indent=1)
 
@@ -268,11 +287,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--stn", action="store_true", help="the STN sampling path: reference / two-pass / one-pass")
     ap.add_argument("--ref", action="store_true", help="time the reference's own CUDA kernels (oracle/_ref) next to ours")
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (device time without launch overhead)")
     ap.add_argument("--batch", type=int, default=5)
     ap.add_argument("--json", default=None)
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"])
     args = ap.parse_args()
+    global GRAPH
+    GRAPH = args.graph
     dt = getattr(torch, args.dtype)
     es = torch.empty(0, dtype=dt).element_size()
     B = args.batch
