@@ -56,6 +56,8 @@ SIGNATURES = {
     "gg_feature_distance_workspace": (_L, [_L, _I, _L]),
     "gg_feature_distance_forward": (_I, [_P] * 5 + [_I, _L, _I, _L, _F, _P]),
     "gg_feature_distance_backward": (_I, [_P] * 6 + [_I, _L, _I, _L, _F, _P]),
+    "gg_bias_relu_pool_nhwc_forward": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _P]),
+    "gg_bias_relu_pool_nhwc_backward": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _P]),
     "gg_to_rgb_nhwc_workspace": (_L, [_L, _I, _L]),
     "gg_to_rgb_nhwc_forward": (_I, [_P] * 5 + [_L, _I, _L, _P]),
     "gg_to_rgb_nhwc_backward": (_I, [_P] * 6 + [_L, _I, _L, _P]),

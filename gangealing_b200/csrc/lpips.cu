@@ -193,6 +193,126 @@ int check_distance(const char* who, int64_t N, int C, int64_t HW) {
   return GG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ VGG slice boundary
+// Between two VGG16 slices the reference runs Conv2d (cuDNN) -> ReLU -> [tap for the distance] -> MaxPool2d(2, 2) -> Conv2d
+// (lpips_backbones.py:106-121 = torchvision features 2-4, 7-9, 14-16, 21-23).  The tap feature map is the largest tensor
+// of its slice and ATen walks it four more times: max_pool forward (read y, write pooled + an int64 index map), max_pool
+// backward (zero-fill + scatter into a full-size gradient), the add of the two gradients that meet at the tap (distance +
+// pool branch), and the ReLU backward.  Here:
+//   forward   raw (conv output, no bias) -> y = relu(raw + bias) AND pooled = maxpool2x2(y), one read of raw
+//   backward  g_raw = [y > 0] * (g_y + [this pixel is the window's FIRST maximum] * g_pooled)  -- the arg-max is recomputed
+//             from the saved y with ATen's rule (scan the window row-major, replace on `>` or NaN: max_pool2d picks the first
+//             maximum), so no index map exists; one pass: read y, g_y, g_pooled (1/4), write g_raw
+// Thread = one 2x2 window x one 16-byte channel vector (4 fp32 / 8 bf16 channels); fp32 arithmetic.  HBM-bound:
+// forward s*N*H*W*C*(1 + 1 + 1/4), backward s*N*H*W*C*(1 + 1 + 1/4 + 1).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_relu_pool_fwd_kernel(T* __restrict__ y, T* __restrict__ pooled, const T* __restrict__ raw, const float* __restrict__ bias,
+                          int cv, int H, int W, int64_t total) {
+  constexpr int V = ChanVec<T>::V;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int cq = static_cast<int>(idx % cv);
+  int64_t t = idx / cv;
+  const int ox = static_cast<int>(t % Wo); t /= Wo;
+  const int oy = static_cast<int>(t % Ho);
+  const int64_t n = t / Ho;
+  const int64_t C = static_cast<int64_t>(cv) * V;
+  const int64_t p00 = ((n * H + 2 * oy) * W + 2 * ox) * C + static_cast<int64_t>(cq) * V;
+  const int64_t off[4] = {p00, p00 + C, p00 + W * C, p00 + W * C + C};
+  uint4 in[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) in[j] = ldg_stream16(raw + off[j]);
+  float b[V];
+#pragma unroll
+  for (int q = 0; q < V / 4; ++q) {
+    const float4 bq = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq * (V / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b[4 * q] = bq.x; b[4 * q + 1] = bq.y; b[4 * q + 2] = bq.z; b[4 * q + 3] = bq.w;
+  }
+  float m[V];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x[V], o[V];
+    ChanVec<T>::unpack(in[j], x);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float v = x[k] + b[k];
+      o[k] = v > 0.f ? v : v * 0.f;          // relu; NaN stays NaN (torch.relu)
+    }
+    const uint4 packed = ChanVec<T>::pack(o);
+    stg_stream16(y + off[j], packed);
+    float r[V];
+    ChanVec<T>::unpack(packed, r);            // pool the STORED (rounded) values: what a separate max_pool2d would read
+#pragma unroll
+    for (int k = 0; k < V; ++k) m[k] = (j == 0 || r[k] > m[k] || r[k] != r[k]) ? r[k] : m[k];
+  }
+  stg_stream16(pooled + ((n * Ho + oy) * Wo + ox) * C + static_cast<int64_t>(cq) * V, ChanVec<T>::pack(m));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_relu_pool_bwd_kernel(T* __restrict__ g_raw, const T* __restrict__ g_y, const T* __restrict__ g_pooled,
+                          const T* __restrict__ y, int cv, int H, int W, int64_t total) {
+  constexpr int V = ChanVec<T>::V;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int cq = static_cast<int>(idx % cv);
+  int64_t t = idx / cv;
+  const int ox = static_cast<int>(t % Wo); t /= Wo;
+  const int oy = static_cast<int>(t % Ho);
+  const int64_t n = t / Ho;
+  const int64_t C = static_cast<int64_t>(cv) * V;
+  const int64_t p00 = ((n * H + 2 * oy) * W + 2 * ox) * C + static_cast<int64_t>(cq) * V;
+  const int64_t off[4] = {p00, p00 + C, p00 + W * C, p00 + W * C + C};
+  uint4 yv[4], gv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    yv[j] = ldg_stream16(y + off[j]);
+    gv[j] = g_y ? ldg_stream16(g_y + off[j]) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float gp[V];
+  if (g_pooled) ChanVec<T>::unpack(ldg_stream16(g_pooled + ((n * Ho + oy) * Wo + ox) * C + static_cast<int64_t>(cq) * V), gp);
+  else {
+#pragma unroll
+    for (int k = 0; k < V; ++k) gp[k] = 0.f;
+  }
+  float yf[4][V];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ChanVec<T>::unpack(yv[j], yf[j]);
+  int arg[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    float m = yf[0][k];
+    int a = 0;
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+      if (yf[j][k] > m || yf[j][k] != yf[j][k]) { m = yf[j][k]; a = j; }
+    arg[k] = a;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float g[V], o[V];
+    ChanVec<T>::unpack(gv[j], g);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float tot = g[k] + (arg[k] == j ? gp[k] : 0.f);
+      o[k] = yf[j][k] > 0.f ? tot : 0.f;      // threshold_backward
+    }
+    stg_stream16(g_raw + off[j], ChanVec<T>::pack(o));
+  }
+}
+
+inline int check_pool(const char* who, int dtype, int64_t N, int C, int H, int W) {
+  if (dtype != GG_F32 && dtype != GG_BF16) return fail(GG_ERR_UNSUPPORTED, "%s: dtype %d not supported (fp32 or bf16)", who, dtype);
+  if (N < 0 || C < 0 || H < 0 || W < 0) return fail(GG_ERR_BAD_ARG, "%s: negative size", who);
+  const int V = dtype == GG_F32 ? 4 : 8;
+  if (C % V != 0) return fail(GG_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of %d (16-byte channel vectors)", who, C, V);
+  if ((H & 1) || (W & 1)) return fail(GG_ERR_UNSUPPORTED, "%s: H=%d, W=%d must be even (2x2 windows, stride 2, no padding)", who, H, W);
+  return GG_OK;
+}
+
 }  // namespace
 }  // namespace gg
 
@@ -253,6 +373,51 @@ int gg_feature_distance_backward(void* g0, void* g1, const float* grad_out, cons
                                               C, HW, eps, static_cast<cudaStream_t>(stream), nullptr);
   if (rc != GG_OK) return rc;
   GG_CHECK_LAUNCH("feature_distance backward launch");
+  return GG_OK;
+}
+
+int gg_bias_relu_pool_nhwc_forward(void* y, void* pooled, const void* raw, const float* bias, int dtype, int64_t N, int C, int H,
+                                   int W, void* stream) {
+  int rc = check_pool("bias_relu_pool", dtype, N, C, H, W);
+  if (rc != GG_OK) return rc;
+  const int V = dtype == GG_F32 ? 4 : 8;
+  const int64_t total = N * (H / 2) * static_cast<int64_t>(W / 2) * (C / V);
+  if (total == 0) return GG_OK;
+  if (!y || !pooled || !raw) return fail(GG_ERR_BAD_ARG, "bias_relu_pool: null tensor");
+  const int64_t grid = (total + 255) / 256;
+  if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "bias_relu_pool: tensor too large");
+  auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == GG_F32)
+    bias_relu_pool_fwd_kernel<float><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<float*>(y), static_cast<float*>(pooled), static_cast<const float*>(raw), bias, C / V, H, W, total);
+  else
+    bias_relu_pool_fwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(pooled), static_cast<const __nv_bfloat16*>(raw), bias, C / V, H,
+        W, total);
+  GG_CHECK_LAUNCH("bias_relu_pool forward launch");
+  return GG_OK;
+}
+
+int gg_bias_relu_pool_nhwc_backward(void* grad_raw, const void* grad_y, const void* grad_pooled, const void* y, int dtype,
+                                    int64_t N, int C, int H, int W, void* stream) {
+  int rc = check_pool("bias_relu_pool backward", dtype, N, C, H, W);
+  if (rc != GG_OK) return rc;
+  const int V = dtype == GG_F32 ? 4 : 8;
+  const int64_t total = N * (H / 2) * static_cast<int64_t>(W / 2) * (C / V);
+  if (total == 0) return GG_OK;
+  if (!grad_raw || !y) return fail(GG_ERR_BAD_ARG, "bias_relu_pool backward: null tensor");
+  const int64_t grid = (total + 255) / 256;
+  if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "bias_relu_pool backward: tensor too large");
+  auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == GG_F32)
+    bias_relu_pool_bwd_kernel<float><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<float*>(grad_raw), static_cast<const float*>(grad_y), static_cast<const float*>(grad_pooled),
+        static_cast<const float*>(y), C / V, H, W, total);
+  else
+    bias_relu_pool_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(grid), 256, 0, st>>>(
+        static_cast<__nv_bfloat16*>(grad_raw), static_cast<const __nv_bfloat16*>(grad_y),
+        static_cast<const __nv_bfloat16*>(grad_pooled), static_cast<const __nv_bfloat16*>(y), C / V, H, W, total);
+  GG_CHECK_LAUNCH("bias_relu_pool backward launch");
   return GG_OK;
 }
 

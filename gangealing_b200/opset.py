@@ -21,6 +21,7 @@ def cuda_ops():
         from .splat2d import splat2d as _splat2d
         from .splat2d import splat2d_lookup as _splat2d_lookup
         from .op import feature_distance as _fd
+        from .op import vgg_pool as _vp
         _cached = types.SimpleNamespace(
             name="sm_100a",
             upfirdn2d=_op.upfirdn2d,
@@ -42,5 +43,7 @@ def cuda_ops():
             splat2d_lookup=_splat2d_lookup,               # uncongeal_points' grid lookup fused into the splat
             nn_argmin=_nn_argmin,                         # congeal_points' brute-force search without the distance tensor
             feature_distance=_fd.feature_distance,
+            bias_relu_pool=_vp.bias_relu_pool,            # VGG slice boundary: bias + ReLU + 2x2 max-pool, one pass each way
+            bias_relu_pool_supported=_vp.supported,
         )
     return _cached

@@ -313,7 +313,12 @@ class ComposedSTN(nn.Module):
         for i, stn in enumerate(self.stns):
             last = i == self.N_minus_1
             if self.num_heads > 1 and warp_policy == "cartesian" and i > 0:
-                policy = self.cluster_assignments.to(source.device).repeat(n, 1)
+                # reference :109 copies the (K, K) identity host -> device on every call; memoised per device here so that the
+                # step stays CUDA-graph capturable (a pageable H2D copy is illegal during capture)
+                eye = getattr(self, "_cluster_assignments_dev", None)
+                if eye is None or eye.device != source.device:
+                    eye = self._cluster_assignments_dev = self.cluster_assignments.to(source.device)
+                policy = eye.repeat(n, 1)
             else:
                 policy = warp_policy
             out, grid, flow_or_matrix = stn(

@@ -66,25 +66,45 @@ class VGG16Slices(nn.Module):
         """ops: the sm_100a op set -> every Conv2d + ReLU pair runs as a bias-free cuDNN convolution followed by ONE
         hand-written bias+ReLU pass (`fused_leaky_relu(x, bias, negative_slope=0, scale=1)` = relu(x + b), the channels-last
         streaming kernel of csrc/nhwc.cu) instead of cuDNN's separate broadcast bias-add kernel + ATen's clamp (two passes
-        over the feature map; 1.2 ms of a 25 ms bf16 step, profiles/r02_step_b32_bf16_launches_v1.txt).  None: plain modules."""
+        over the feature map; 1.2 ms of a 25 ms bf16 step, profiles/r02_step_b32_bf16_launches_v1.txt); at a slice boundary
+        (ReLU -> tap -> MaxPool2d of the next slice) the bias+ReLU pass also emits the pooled map and the backward of
+        pool + gradient add + ReLU is one pass (op/vgg_pool.py).  None: plain modules."""
         outs = []
-        for s in self.slices():
+        slices = self.slices()
+        pooled = None          # the NEXT slice's MaxPool2d output, when the fused boundary kernel already produced it
+        for k, s in enumerate(slices):
             if ops is None or not x.is_cuda:
                 x = s(x)
             else:
                 layers = list(s.children())
+                nxt = list(slices[k + 1].children()) if k + 1 < len(slices) else []
+                pool_next = bool(nxt) and isinstance(nxt[0], nn.MaxPool2d) and _is_2x2_pool(nxt[0]) and hasattr(ops, "bias_relu_pool")
                 i = 0
+                if pooled is not None:            # this slice's leading MaxPool2d ran inside the previous slice's last kernel
+                    x, pooled, i = pooled, None, 1
                 while i < len(layers):
                     m = layers[i]
                     if isinstance(m, nn.Conv2d) and i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU):
                         x = nn.functional.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
-                        x = ops.fused_leaky_relu(x, m.bias.float() if m.bias.dtype != torch.float32 else m.bias, 0.0, 1.0)
+                        bias = m.bias.float() if m.bias.dtype != torch.float32 else m.bias
+                        if i + 2 == len(layers) and pool_next and ops.bias_relu_pool_supported(x):
+                            # slice boundary: relu(x + b) (the tapped feature map) AND its 2x2 max-pool in one pass
+                            x, pooled = ops.bias_relu_pool(x, bias)
+                        else:
+                            x = ops.fused_leaky_relu(x, bias, 0.0, 1.0)
                         i += 2
                     else:
                         x = m(x)
                         i += 1
             outs.append(x)
         return outs
+
+
+def _is_2x2_pool(m):
+    def pair(v):
+        return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    return (pair(m.kernel_size) == (2, 2) and pair(m.stride) == (2, 2) and pair(m.padding) == (0, 0) and pair(m.dilation) == (1, 1)
+            and not m.ceil_mode and not m.return_indices)
 
 
 class ScalingLayer(nn.Module):

@@ -350,6 +350,18 @@ GG_API int gg_feature_distance_backward(void* g0, void* g1, const float* grad_ou
                                         const float* weight, int dtype, int64_t N, int C, int64_t HW, float eps,
                                         void* stream);
 
+/* VGG16 slice boundary of the perceptual loss: Conv2d -> ReLU -> [tap] -> MaxPool2d(2, 2) -> Conv2d
+ * (reference models/losses/lpips_backbones.py:106-121 = torchvision vgg16().features 2-4, 7-9, 14-16, 21-23; ATen
+ * threshold / max_pool2d_with_indices and their backwards).  One pass each on channels-last maps:
+ *   forward : y = relu(raw + bias[c]) (N, H, W, C) and pooled = max over 2x2 windows, stride 2 (N, H/2, W/2, C)
+ *   backward: grad_raw = [y > 0] * (grad_y + [pixel is the FIRST maximum of its window, row-major] * grad_pooled);
+ *             grad_y / grad_pooled may be NULL (= 0).  No index map: the arg-max is recomputed from y with ATen's rule.
+ * raw / y / pooled / grads: `dtype` = GG_F32 or GG_BF16; bias: (C) fp32 or NULL; C % (16 / sizeof(dtype)) == 0; H, W even. */
+GG_API int gg_bias_relu_pool_nhwc_forward(void* y, void* pooled, const void* raw, const float* bias, int dtype, int64_t N,
+                                          int C, int H, int W, void* stream);
+GG_API int gg_bias_relu_pool_nhwc_backward(void* grad_raw, const void* grad_y, const void* grad_pooled, const void* y,
+                                           int dtype, int64_t N, int C, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * BilinearDownsample: reference models/spatial_transformers/antialiased_sampling.py:241-256 --
  * ReflectionPad2d(stride/2) + depthwise 1x2s conv, stride (1,s) + depthwise 2sx1 conv, stride (s,1).  One gather:

@@ -140,3 +140,70 @@ def test_whole_perceptual_loss_matches_the_reference_lpips_fixture():
     g0, g1 = torch.autograd.grad(val.sum(), [in0, in1])
     assert_close(g0, blob["g0"], rtol=1e-4, what="d/d in0")
     assert_close(g1, blob["g1"], rtol=1e-4, what="d/d in1")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,shape", [(torch.float32, (2, 64, 32, 32)), (torch.float32, (3, 128, 6, 10)), (torch.float32, (1, 512, 2, 2)),
+                                         (torch.bfloat16, (2, 64, 32, 32)), (torch.bfloat16, (2, 256, 8, 4))])
+@pytest.mark.parametrize("ties", [False, True])
+def test_bias_relu_pool_matches_the_aten_sequence_of_the_reference_backbone(dtype, shape, ties):
+    """VGG slice boundary (Conv2d -> ReLU -> [tap] -> MaxPool2d(2,2), lpips_backbones.py:106-121) in one pass each way vs the
+    ATen sequence on the CPU.  `ties`: small-integer data, so windows hold EQUAL maxima -- the gradient must go to the first
+    one in row-major order (max_pool2d's rule) -- and exact zeros after the ReLU; every value is exactly representable, so
+    forward, pooled map and gradients must then be BIT-EXACT."""
+    from gangealing_b200.op.vgg_pool import bias_relu_pool
+    from oracle.perceptual import bias_relu_pool_ref
+    g = torch.Generator().manual_seed(shape[1] + shape[2] + int(ties))
+    n, c, h, w = shape
+    if ties:
+        raw = torch.randint(-3, 4, shape, generator=g).float()
+        bias = torch.randint(-1, 2, (c,), generator=g).float()
+        gy = torch.randint(-4, 5, shape, generator=g).float()
+        gp = torch.randint(-4, 5, (n, c, h // 2, w // 2), generator=g).float()
+    else:
+        raw, bias = torch.randn(shape, generator=g), torch.randn(c, generator=g)
+        gy, gp = torch.randn(shape, generator=g), torch.randn(n, c, h // 2, w // 2, generator=g)
+    raw, gy, gp = raw.to(dtype), gy.to(dtype), gp.to(dtype)        # bf16 inputs are the rounded values on both sides
+    a = raw.clone().requires_grad_(True)
+    y_ref, p_ref = bias_relu_pool_ref(a.float() if dtype == torch.bfloat16 else a, bias)
+    if dtype == torch.bfloat16:   # the backbone stores bf16 feature maps: the pool reads the ROUNDED activation
+        y_ref = y_ref.to(dtype).float()
+        p_ref = torch.nn.functional.max_pool2d(y_ref, 2, 2)
+    b = raw.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y, p = bias_relu_pool(b, bias.to(DEV))
+    assert y.dtype == dtype and p.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    exact = ties or dtype == torch.float32
+    if exact:
+        assert torch.equal(y.float().cpu(), y_ref.detach().float()) and torch.equal(p.float().cpu(), p_ref.detach().float())
+    else:
+        assert_close(y.float(), y_ref, rtol=8e-3, what="relu(raw + bias)")
+        assert_close(p.float(), p_ref, rtol=8e-3, what="pooled")
+    (ga,) = torch.autograd.grad([y_ref, p_ref], [a], [gy.float(), gp.float()]) if dtype == torch.float32 else (None,)
+    (gb,) = torch.autograd.grad([y, p], [b], [gy.to(DEV), gp.to(DEV)])
+    if dtype == torch.float32:
+        if ties:
+            assert torch.equal(gb.cpu(), ga)
+        assert_close(gb, ga, rtol=1e-6, what="gradient")
+    elif ties:    # bf16 with integers: reference gradient from the fp32 graph of the same (exact) values
+        a32 = raw.float().clone().requires_grad_(True)
+        y32, p32 = bias_relu_pool_ref(a32, bias)
+        (g32,) = torch.autograd.grad([y32, p32], [a32], [gy.float(), gp.float()])
+        assert torch.equal(gb.float().cpu(), g32)
+    # only one of the two gradients arriving (the other branch unused)
+    (g_only_pool,) = torch.autograd.grad(bias_relu_pool(b, bias.to(DEV))[1], [b], [gp.to(DEV)])
+    a2 = raw.float().clone().requires_grad_(True)
+    (g_ref_pool,) = torch.autograd.grad(bias_relu_pool_ref(a2, bias)[1] if dtype == torch.float32 else
+                                        torch.nn.functional.max_pool2d(torch.relu(a2 + bias.reshape(1, -1, 1, 1)), 2, 2), [a2], [gp.float()])
+    if exact:
+        assert_close(g_only_pool.float(), g_ref_pool, rtol=1e-6, what="pool-only gradient")
+
+
+@pytest.mark.gpu
+def test_bias_relu_pool_argument_checks():
+    from gangealing_b200.op.vgg_pool import bias_relu_pool, supported
+    x = torch.randn(1, 64, 5, 4, device=DEV)
+    assert not supported(x) and supported(torch.randn(1, 64, 4, 4, device=DEV)) and not supported(torch.randn(1, 6, 4, 4, device=DEV))
+    with pytest.raises(RuntimeError):
+        bias_relu_pool(x, None)
+    with pytest.raises(RuntimeError):
+        bias_relu_pool(torch.randn(1, 64, 4, 4), None)      # no CPU path

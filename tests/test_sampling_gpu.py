@@ -170,7 +170,12 @@ def test_sampler_integer_work_is_bit_exact(mode, hs, ws):
         if name == "dyadic":
             corner_ok = torch.ones_like(x0, dtype=torch.bool)
         else:
-            corner_ok = ((ix - ix.round()).abs() > 1e-4) & ((iy - iy.round()).abs() > 1e-4)
+            def decided(c, size):      # not within 1e-4 px of an integer -- or pinned to a border pixel by the clamp of the
+                ok = (c - c.round()).abs() > 1e-4                      # border / reflection modes (an exact constant on both sides)
+                if mode != "zeros":
+                    ok |= (c == 0) | (c == size - 1)
+                return ok
+            corner_ok = decided(ix, ws) & decided(iy, hs)
             assert corner_ok.float().mean() > 0.995
         assert torch.equal(got[..., 0][corner_ok].long(), x0[corner_ok]), name + " x0"
         assert torch.equal(got[..., 1][corner_ok].long(), y0[corner_ok]), name + " y0"

@@ -128,7 +128,8 @@ def reference_bar(B, dev, k4, timeit, pool_count, peak, json_path):
         n, c, h, w = x.shape
         return up_ref.upfirdn2d(x.reshape(-1, h, w, 1), k4, up, up, down, down, pad[0], pad[1], pad[0], pad[1])
 
-    for C, H in [(128, 256), (256, 128), (512, 64), (512, 32), (512, 16), (512, 8)]:
+    only = os.environ.get("GG_OPBENCH_ONLY", "")      # e.g. "splat": just those rows (kernel experiments)
+    for C, H in ([] if only else [(128, 256), (256, 128), (512, 64), (512, 32), (512, 16), (512, 8)]):
         hin = H + 1
         nbytes = 4 * B * C * (hin * hin + H * H)
         P = pool_count(nbytes)
@@ -170,11 +171,11 @@ def reference_bar(B, dev, k4, timeit, pool_count, peak, json_path):
             timeit(ref_bwd, P), timeit(lambda i: bias_act_backward_raw(ys[i], ys[(i + 1) % P], 0.2, 2 ** 0.5, True), P),
             timeit(lambda i: bias_act_backward_raw(yl[i], yl[(i + 1) % P], 0.2, 2 ** 0.5, True), P))
         del ys, yl
-    for H in (128, 64):
+    for H in ([] if only else (128, 64)):
         x = torch.randn(B, 3, H, H, device=dev)
         add("upfirdn2d rgb up2 %d->%d" % (H, 2 * H), 4 * B * 3 * 5 * H * H,
             timeit(lambda i: ref_up(x, 2, 1, (2, 1)), 1), timeit(lambda i: op.upfirdn2d(x, k4, up=2, pad=(2, 1)), 1), None)
-    for C, H, pad in [(64, 128, (2, 2)), (64, 128, (1, 1)), (128, 64, (2, 2)), (512, 32, (2, 2))]:
+    for C, H, pad in ([] if only else [(64, 128, (2, 2)), (64, 128, (1, 1)), (128, 64, (2, 2)), (512, 32, (2, 2))]):
         x = [torch.randn(B, C, H, H, device=dev) for _ in range(4)]
         xl = [t.contiguous(memory_format=CL) for t in x]
         ho = H + 2 * pad[0] - 3
