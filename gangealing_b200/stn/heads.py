@@ -167,7 +167,7 @@ class FlowHead(nn.Module):
         n, _, h, w, _ = low.size()
         if isinstance(warp_policy, torch.Tensor):
             assignments = warp_policy.max(dim=1).indices % self.num_heads
-            pick = torch.arange(n)
+            pick = torch.arange(n, device=low.device)   # on the device: indexing with a CPU tensor is a pageable H2D copy (not capturable)
             low, mask = low[pick, assignments], mask[pick, assignments]
             split = 1
         elif warp_policy == "cartesian":

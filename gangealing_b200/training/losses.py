@@ -62,4 +62,4 @@ def gangealing_cluster_loss(generator, stn, ll, loss_fn, resize_fake2stn, psi, b
         delta_flow = delta_flow.view(2, batch, num_heads, *hw2).permute(1, 0, 2, 3, 4, 5).reshape(batch, 2 * num_heads, *hw2)
     else:
         delta_flow = delta_flow.view(batch, num_heads, *hw2)
-    return assignments.values.mean(), delta_flow[torch.arange(batch), assignments.indices]
+    return assignments.values.mean(), delta_flow[torch.arange(batch, device=delta_flow.device), assignments.indices]
