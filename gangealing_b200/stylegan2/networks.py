@@ -79,8 +79,9 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
         self.ops = ops if ops is not None else cuda_ops()
 
-    def forward(self, input):
-        w = self.weight * self.scale
+    def forward(self, input, gain=1.0):
+        """`gain`: extra output scale folded into the equalised-lr weight scale (ResBlock folds its 1/sqrt(2) here)."""
+        w = self.weight * (self.scale * gain)
         b = self.bias
         if w.dtype != input.dtype:      # bf16 activations (BASELINE config 3): fp32 master weights, bf16 tensor-core conv
             w = w.to(input.dtype)
@@ -314,6 +315,23 @@ class ResBlock(nn.Module):
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=downsample, activate=False, bias=False, ops=ops)
 
     def forward(self, input):
+        """(conv2(conv1(x)) + skip(x)) / sqrt(2)   (reference networks.py:638-657).  On the sm_100a op set the 1/sqrt(2) is
+        folded into the two branches -- the gain of conv2's fused bias+lrelu pass and the skip convolution's weight scale --
+        so the block ends in ONE add instead of add + divide (and its backward loses the matching multiply): two
+        activation-sized passes less per block and direction."""
+        act, skip_conv = self.conv2[-1], self.skip[-1]
+        if (input.is_cuda and isinstance(act, FusedLeakyReLU) and getattr(act.ops, "name", None) == "sm_100a"
+                and isinstance(skip_conv, EqualConv2d) and skip_conv.bias is None):
+            inv = 1.0 / math.sqrt(2)
+            main = self.conv1(input)
+            for layer in list(self.conv2)[:-1]:
+                main = layer(main)
+            bias = act.bias if main.dtype == torch.bfloat16 else act.bias.type(main.dtype)   # as FusedLeakyReLU.forward
+            main = act.ops.fused_leaky_relu(main, bias, act.negative_slope, act.scale * inv)
+            side = input
+            for layer in list(self.skip)[:-1]:
+                side = layer(side)
+            return main + skip_conv(side, gain=inv)
         return (self.conv2(self.conv1(input)) + self.skip(input)) / math.sqrt(2)
 
 
