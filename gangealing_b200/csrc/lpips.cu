@@ -205,6 +205,28 @@ int check_distance(const char* who, int64_t N, int C, int64_t HW) {
 //             maximum), so no index map exists; one pass: read y, g_y, g_pooled (1/4), write g_raw
 // Thread = one 2x2 window x one 16-byte channel vector (4 fp32 / 8 bf16 channels); fp32 arithmetic.  HBM-bound:
 // forward s*N*H*W*C*(1 + 1 + 1/4), backward s*N*H*W*C*(1 + 1 + 1/4 + 1).
+// idx -> (channel vector, window x, window y, sample); 32-bit divisions whenever the tensor allows it (64-bit ones cost ~80
+// instructions each)
+__device__ __forceinline__ void decode_window(int64_t idx, int64_t total, int cv, int Wo, int Ho, int& cq, int& ox, int& oy,
+                                              int64_t& n) {
+  if (total <= 0xffffffffLL) {
+    unsigned t = static_cast<unsigned>(idx);
+    unsigned q = t / static_cast<unsigned>(cv);
+    cq = static_cast<int>(t - q * static_cast<unsigned>(cv)); t = q;
+    q = t / static_cast<unsigned>(Wo);
+    ox = static_cast<int>(t - q * static_cast<unsigned>(Wo)); t = q;
+    q = t / static_cast<unsigned>(Ho);
+    oy = static_cast<int>(t - q * static_cast<unsigned>(Ho));
+    n = q;
+  } else {
+    cq = static_cast<int>(idx % cv);
+    int64_t t = idx / cv;
+    ox = static_cast<int>(t % Wo); t /= Wo;
+    oy = static_cast<int>(t % Ho);
+    n = t / Ho;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 bias_relu_pool_fwd_kernel(T* __restrict__ y, T* __restrict__ pooled, const T* __restrict__ raw, const float* __restrict__ bias,
@@ -213,11 +235,9 @@ bias_relu_pool_fwd_kernel(T* __restrict__ y, T* __restrict__ pooled, const T* __
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int Ho = H >> 1, Wo = W >> 1;
-  const int cq = static_cast<int>(idx % cv);
-  int64_t t = idx / cv;
-  const int ox = static_cast<int>(t % Wo); t /= Wo;
-  const int oy = static_cast<int>(t % Ho);
-  const int64_t n = t / Ho;
+  int cq, ox, oy;
+  int64_t n;
+  decode_window(idx, total, cv, Wo, Ho, cq, ox, oy, n);
   const int64_t C = static_cast<int64_t>(cv) * V;
   const int64_t p00 = ((n * H + 2 * oy) * W + 2 * ox) * C + static_cast<int64_t>(cq) * V;
   const int64_t off[4] = {p00, p00 + C, p00 + W * C, p00 + W * C + C};
@@ -258,11 +278,9 @@ bias_relu_pool_bwd_kernel(T* __restrict__ g_raw, const T* __restrict__ g_y, cons
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int Ho = H >> 1, Wo = W >> 1;
-  const int cq = static_cast<int>(idx % cv);
-  int64_t t = idx / cv;
-  const int ox = static_cast<int>(t % Wo); t /= Wo;
-  const int oy = static_cast<int>(t % Ho);
-  const int64_t n = t / Ho;
+  int cq, ox, oy;
+  int64_t n;
+  decode_window(idx, total, cv, Wo, Ho, cq, ox, oy, n);
   const int64_t C = static_cast<int64_t>(cv) * V;
   const int64_t p00 = ((n * H + 2 * oy) * W + 2 * ox) * C + static_cast<int64_t>(cq) * V;
   const int64_t off[4] = {p00, p00 + C, p00 + W * C, p00 + W * C + C};

@@ -45,9 +45,21 @@ noise_bias_act_nhwc_kernel(T* __restrict__ out, const T* __restrict__ x, const f
   for (int u = 0; u < 4; ++u) {
     const int64_t v = base + static_cast<int64_t>(u) * kT;
     if (v < n_vec) {
-      const int64_t pix = v / cv;                      // n*hw + p
-      const int cq = static_cast<int>(v - pix * cv);
-      const int64_t n = pix / hw;
+      // index arithmetic in 32 bits whenever the tensor allows it (a 64-bit division costs ~80 instructions: with two of
+      // them per vector this streaming kernel was ISSUE-bound in bf16, 83 % issue utilisation at 80 % of the HBM peak);
+      // the sample index is only needed for the per-(sample, channel) row scale
+      int64_t pix, n = 0;
+      int cq;
+      if (n_vec <= 0xffffffffLL) {
+        const unsigned v32 = static_cast<unsigned>(v), p32 = v32 / static_cast<unsigned>(cv);
+        cq = static_cast<int>(v32 - p32 * static_cast<unsigned>(cv));
+        pix = p32;
+        if (row_scale) n = p32 / static_cast<unsigned>(hw);
+      } else {
+        pix = v / cv;
+        cq = static_cast<int>(v - pix * cv);
+        if (row_scale) n = pix / hw;
+      }
       const float nz = noise ? nw * __ldg(noise + pix) : 0.f;
       float xf[V], o[V];
       ChanVec<T>::unpack(xv[u], xf);
