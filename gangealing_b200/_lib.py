@@ -64,6 +64,7 @@ SIGNATURES = {
     "gg_nn_argmin_workspace": (_L, [_L, _L]),
     "gg_nn_argmin": (_I, [_P, _P, _P, _P, _L, _L, _I, _P]),
     "gg_splat2d_lookup_forward": (_I, [_P] * 8 + [_L, _L, _I, _I, _I, _I, _I, _F, _F, _I, _P]),
+    "gg_scale_cast_multi": (_I, [_P, _P, _P, _I, _I, _P]),
     "gg_adam_ema_step": (_I, [_P, _P, _P, _I, _I, _P, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _P]),
     "gg_tv_loss_workspace": (_L, [_L, _I, _I]),
     "gg_tv_loss_forward": (_I, [_P, _P, _P, _L, _I, _I, _P]),
@@ -208,3 +209,22 @@ def stream():
 
 def sm_count():
     return load().gg_sm_count()
+
+
+def ship_table(slot, payload):
+    """Copy a small CPU tensor `payload` into the pinned buffer slot["host"] and on to slot["dev"] (async, current stream).
+    The pinned buffer is reused every step, and in an eager loop the host may run a whole step ahead of the GPU: before it
+    is overwritten, wait for the previous copy OUT of it (an event recorded right after that copy).  Inside a CUDA-graph
+    capture no event is recorded (captured events cannot be waited on; the table is shipped once per capture anyway)."""
+    ev = slot.get("event")
+    if ev is not None:
+        ev.synchronize()
+    slot["host"].copy_(payload)
+    slot["dev"].copy_(slot["host"], non_blocking=True)
+    if torch.cuda.is_current_stream_capturing():
+        slot["event"] = None
+    else:
+        ev = torch.cuda.Event()
+        ev.record()
+        slot["event"] = ev
+

@@ -84,6 +84,65 @@ adam_ema_kernel(const AdamTensor* __restrict__ table, const int* __restrict__ bl
   }
 }
 
+// ------------------------------------------------------------------------------------------------ equalised-lr weights
+// gg_scale_cast_multi   reference networks.py:121-127,146-149 (`self.weight * self.scale` inside EVERY EqualConv2d /
+//                       EqualLinear forward): one ATen multiply per layer forward and one per layer backward -- 124
+//                       parameter-sized launches per step at ~3.6 us each, plus a cast each way with bf16 activations.
+//                       Here: dst[i] = (dst type) (src[i] * scale) for a whole TABLE of tensors in one launch; used forward
+//                       (fp32 master weight -> scaled weight in the convolution's dtype) and backward (gradient of the scaled
+//                       weight, fp32 or bf16 -> fp32 gradient of the master weight) by op/scaled_weights.py.
+struct ScaleTensor {          // one row of the device-resident table (4 x 8 bytes)
+  const void* src; void* dst;
+  int64_t numel;
+  float scale;
+  int dtypes;                 // src dtype | dst dtype << 8   (GG_F32 / GG_BF16)
+};
+
+__device__ __forceinline__ float ld_as_float(const void* p, int dt, int64_t i) {
+  return dt == GG_F32 ? static_cast<const float*>(p)[i] : __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st_from_float(void* p, int dt, int64_t i, float v) {
+  if (dt == GG_F32) static_cast<float*>(p)[i] = v;
+  else static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(kAdamThreads)
+scale_cast_multi_kernel(const ScaleTensor* __restrict__ table, const int* __restrict__ block_tensor,
+                        const int* __restrict__ block_chunk, int chunk) {
+  const ScaleTensor t = table[block_tensor[blockIdx.x]];
+  const int64_t e0 = static_cast<int64_t>(block_chunk[blockIdx.x]) * chunk;
+  const int64_t e1 = min(e0 + static_cast<int64_t>(chunk), t.numel);
+  const int sdt = t.dtypes & 0xff, ddt = (t.dtypes >> 8) & 0xff;
+  const bool vec = ((reinterpret_cast<uintptr_t>(t.src) | reinterpret_cast<uintptr_t>(t.dst)) & 15) == 0 && (e0 & 3) == 0;
+  int64_t done = e0;
+  if (vec) {
+    const int64_t n4 = (e1 - e0) >> 2;
+    for (int64_t i = threadIdx.x; i < n4; i += kAdamThreads) {
+      const int64_t o = e0 + i * 4;
+      float v[4];
+      if (sdt == GG_F32) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(t.src) + o));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      } else {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(t.src) + o));
+        v[0] = __uint_as_float(a.x << 16); v[1] = __uint_as_float(a.x & 0xffff0000u);
+        v[2] = __uint_as_float(a.y << 16); v[3] = __uint_as_float(a.y & 0xffff0000u);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] *= t.scale;
+      if (ddt == GG_F32) {
+        *reinterpret_cast<float4*>(static_cast<float*>(t.dst) + o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(t.dst) + o) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+    }
+    done = e0 + n4 * 4;
+  }
+  for (int64_t o = done + threadIdx.x; o < e1; o += kAdamThreads) st_from_float(t.dst, ddt, o, ld_as_float(t.src, sdt, o) * t.scale);
+}
+
 // ------------------------------------------------------------------------------------------------ total variation
 __device__ __forceinline__ float huber(float d) {            // loss.py:7: where(a <= 1, 0.5 a^2, a - 0.5), a = |d|
   const float a = fabsf(d);
@@ -166,6 +225,17 @@ inline int tv_blocks(int64_t total) {
 using namespace gg;
 
 extern "C" {
+
+int gg_scale_cast_multi(const void* table, const int* block_tensor, const int* block_chunk, int blocks, int chunk,
+                        void* stream) {
+  if (blocks < 0 || chunk < 4 || (chunk & 3)) return fail(GG_ERR_BAD_ARG, "scale_cast_multi: bad geometry (chunk must be a multiple of 4)");
+  if (blocks == 0) return GG_OK;
+  if (!table || !block_tensor || !block_chunk) return fail(GG_ERR_BAD_ARG, "scale_cast_multi: null table");
+  scale_cast_multi_kernel<<<static_cast<unsigned>(blocks), kAdamThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const ScaleTensor*>(table), block_tensor, block_chunk, chunk);
+  GG_CHECK_LAUNCH("scale_cast_multi launch");
+  return GG_OK;
+}
 
 int gg_adam_ema_step(const void* table, const int* block_tensor, const int* block_chunk, int blocks, int chunk,
                      float* state, double beta1, double beta2, double eps, double ema_decay, void* stream) {

@@ -79,13 +79,18 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
         self.ops = ops if ops is not None else cuda_ops()
 
+    scaler = None     # op/scaled_weights.WeightScaler of the training step, or None (set per instance by the Trainer)
+
     def forward(self, input, gain=1.0):
         """`gain`: extra output scale folded into the equalised-lr weight scale (ResBlock folds its 1/sqrt(2) here)."""
-        w = self.weight * (self.scale * gain)
+        w = self.scaler.get(self, input.dtype, gain) if self.scaler is not None and input.is_cuda else None
+        if w is None:
+            w = self.weight * (self.scale * gain)
         b = self.bias
         if w.dtype != input.dtype:      # bf16 activations (BASELINE config 3): fp32 master weights, bf16 tensor-core conv
             w = w.to(input.dtype)
-            b = b.to(input.dtype) if b is not None else None
+        if b is not None and b.dtype != input.dtype:
+            b = b.to(input.dtype)
         return self.ops.conv2d(input, w, bias=b, stride=self.stride, padding=self.padding)
 
     def __repr__(self):
@@ -103,11 +108,16 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
         self.ops = ops if ops is not None else cuda_ops()
 
+    scaler = None     # see EqualConv2d.scaler
+
     def forward(self, input):
+        w = self.scaler.get(self, input.dtype) if self.scaler is not None and input.is_cuda else None
+        if w is None:
+            w = self.weight * self.scale
         if self.activation:
-            out = F.linear(input, self.weight * self.scale)
+            out = F.linear(input, w)
             return self.ops.fused_leaky_relu(out, self.bias * self.lr_mul)
-        return F.linear(input, self.weight * self.scale, bias=self.bias * self.lr_mul)
+        return F.linear(input, w, bias=self.bias * self.lr_mul)
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"

@@ -55,6 +55,7 @@ class FusedAdamEMA(torch.optim.Optimizer):
         self._table_host = torch.zeros((len(self._order), 7), dtype=torch.int64).pin_memory()
         self._table = torch.zeros((len(self._order), 7), dtype=torch.int64, device=self.device)
         self._table_key = None
+        self._ship = {"host": self._table_host, "dev": self._table}
 
     # ---- schedule ------------------------------------------------------------------------------------------------
     def set_lr(self, group, value):
@@ -91,8 +92,7 @@ class FusedAdamEMA(torch.optim.Optimizer):
             key.append(g.data_ptr())
         key = tuple(key)
         if key != self._table_key:
-            self._table_host.copy_(torch.tensor(rows, dtype=torch.int64))
-            self._table.copy_(self._table_host, non_blocking=True)
+            _lib.ship_table(self._ship, torch.tensor(rows, dtype=torch.int64))
             self._table_key = key
 
     @torch.no_grad()

@@ -4,6 +4,7 @@ Trainer.step() = gangealing_loss forward (G x2, STN, perceptual) -> TV / identit
 (DDP all-reduces the STN gradients over NCCL) -> Adam x2 -> EMA of the STN -> loss reduce.  It is what bench.py
 times for the "train images/sec at 256^2" metric.
 """
+import contextlib
 import dataclasses
 
 import torch
@@ -63,6 +64,8 @@ class TrainConfig:
     #                                   trunk / VGG activations; fp32 master weights, fp32 arithmetic in the fused kernels,
     #                                   bf16 tensor-core convolutions, fp32 images / grids / losses / optimiser
     fused_optimizer: bool = True      # CUDA: Adam x2 + EMA as ONE multi-tensor kernel (training/fused_optim.py)
+    fused_weight_scaling: bool = True  # CUDA: the STN's 62 `weight * scale` products (and their backward) as a few multi-tensor
+    #                                    launches per step (op/scaled_weights.py)
     grad_compression: str = "none"    # DDP gradient all-reduce: "none" (fp32) or "bf16" (compressed on the wire)
     bucket_cap_mb: int = 25
 
@@ -164,6 +167,14 @@ class Trainer:
                                       eps=1e-8, fused=fused, capturable=fused)
             self.ll_optim = optim.Adam(self.ll_module.parameters(), lr=self.ll_lr_t if fused else cfg.ll_lr, betas=(0.9, 0.999),
                                        eps=1e-8, fused=fused, capturable=fused)
+        self.weight_scaler = None
+        if fused and ops is None and cfg.fused_weight_scaling:
+            from ..op.scaled_weights import WeightScaler, equalized_layers
+            layers = equalized_layers(self.t_module)
+            if layers:
+                self.weight_scaler = WeightScaler(layers)
+                for module, _ in layers:
+                    module.scaler = self.weight_scaler
         self._graph = None
         self.zero = torch.tensor(0.0, device=device)
         # each rank draws its own latents (reference train.py:193: seed*world + rank)
@@ -254,11 +265,14 @@ class Trainer:
 
     def _eager_step(self, z=None):
         cfg = self.cfg
-        loss_dict = self.losses(z)
-        self.t_optim.zero_grad(set_to_none=True)
-        self.ll_optim.zero_grad(set_to_none=True)
-        full = loss_dict["p"] + cfg.tv_weight * loss_dict["tv"] + cfg.flow_identity_weight * loss_dict["f"]
-        full.backward()
+        # the scaled-weight cache is valid for exactly one forward + backward: the optimiser below changes the parameters
+        scope = self.weight_scaler.step() if self.weight_scaler is not None else contextlib.nullcontext()
+        with scope:
+            loss_dict = self.losses(z)
+            self.t_optim.zero_grad(set_to_none=True)
+            self.ll_optim.zero_grad(set_to_none=True)
+            full = loss_dict["p"] + cfg.tv_weight * loss_dict["tv"] + cfg.flow_identity_weight * loss_dict["f"]
+            full.backward()
         if self.fused_optim is not None:
             self.fused_optim.step()               # Adam (both groups) + EMA: one multi-tensor kernel
         else:

@@ -410,6 +410,16 @@ GG_API int gg_tv_loss_forward(float* out, void* workspace, const float* flow, in
 GG_API int gg_tv_loss_backward(float* grad_flow, const float* grad_out, const float* flow, int64_t N, int H, int W,
                                void* stream);
 
+/* Equalised-learning-rate weights of a whole network in one launch: reference networks.py:121-127 (EqualConv2d) and :146-149
+ * (EqualLinear) multiply `self.weight * self.scale` inside every forward (and autograd multiplies again in every backward).
+ *   for each table row t:  dst_t[i] = (dst dtype) (src_t[i] * scale_t),  i < numel_t
+ * table: device array of rows {const void* src; void* dst; int64 numel; float scale; int32 dtypes = src_dtype | dst_dtype << 8}
+ * (32 bytes; dtypes GG_F32 / GG_BF16); CTA b handles elements [block_chunk[b]*chunk, +chunk) of tensor block_tensor[b]
+ * (chunk a multiple of 4).  Forward: fp32 master weights -> scaled weights in the convolution's dtype; backward: gradients of
+ * the scaled weights -> fp32 gradients of the master weights. */
+GG_API int gg_scale_cast_multi(const void* table, const int* block_tensor, const int* block_chunk, int blocks, int chunk,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
