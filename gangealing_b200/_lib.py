@@ -215,13 +215,15 @@ def ship_table(slot, payload):
     """Copy a small CPU tensor `payload` into the pinned buffer slot["host"] and on to slot["dev"] (async, current stream).
     The pinned buffer is reused every step, and in an eager loop the host may run a whole step ahead of the GPU: before it
     is overwritten, wait for the previous copy OUT of it (an event recorded right after that copy).  Inside a CUDA-graph
-    capture no event is recorded (captured events cannot be waited on; the table is shipped once per capture anyway)."""
+    capture no event is recorded or waited on (the table is shipped once per capture; replays re-read the pinned buffer,
+    which nothing rewrites while pointers stay put)."""
+    capturing = torch.cuda.is_current_stream_capturing()
     ev = slot.get("event")
-    if ev is not None:
-        ev.synchronize()
+    if ev is not None and not capturing:   # event waits are illegal while a (global-mode) capture is open; torch.cuda.graph
+        ev.synchronize()                   # synchronises the device before it starts capturing, so nothing is in flight then
     slot["host"].copy_(payload)
     slot["dev"].copy_(slot["host"], non_blocking=True)
-    if torch.cuda.is_current_stream_capturing():
+    if capturing:
         slot["event"] = None
     else:
         ev = torch.cuda.Event()

@@ -125,7 +125,7 @@ def test_multi_tensor_weight_scaling_equals_the_per_layer_products(dtype):
     loss and the same gradients -- same fp32 multiply, same rounding -- up to cuDNN's run-to-run noise."""
     import contextlib
     from gangealing_b200.training import TrainConfig, Trainer
-    cfg = TrainConfig(gen_size=64, flow_size=32, dim_latent=32, n_mlp=2, batch=2, inject=3, gen_channel_multiplier=1,
+    cfg = TrainConfig(gen_size=128, flow_size=64, dim_latent=32, n_mlp=2, batch=2, inject=3, gen_channel_multiplier=1,
                       stn_channel_multiplier=0.25, tv_weight=10.0, dtype=dtype)
     tr = Trainer(cfg, DEV)
     sc = tr.weight_scaler
