@@ -79,3 +79,56 @@ def feature_distance(f0, f1, weight=None, eps=1e-10):
     if a.dtype != b.dtype:
         a, b = a.float(), b.float()
     return _FeatureDistance.apply(a, b, weight, float(eps))
+
+
+class _FeatureDistanceStacked(Function):
+    """feature_distance(f[:N], f[N:]) on ONE stacked (2N, C, H, W) channels-last map: the two halves are the two images'
+    features of a single backbone pass; the gradient is written straight into the halves of one (2N, ...) tensor (slicing the
+    halves out with autograd would zero-fill and copy each half's gradient into a full-size tensor again)."""
+
+    @staticmethod
+    def forward(ctx, f, weight, eps):
+        _lib.require_cuda(f, weight)
+        n2, c, h, w = f.shape
+        n = n2 // 2
+        lib = _lib.load()
+        wt = weight.detach().float().reshape(-1).contiguous() if weight is not None else None
+        out = torch.empty(n, dtype=torch.float32, device=f.device)
+        ws = torch.empty(max(1, lib.gg_feature_distance_workspace(n, c, h * w) // 4), dtype=torch.float32, device=f.device)
+        half = n * c * h * w * f.element_size()
+        rc = lib.gg_feature_distance_forward(out.data_ptr(), ws.data_ptr(), f.data_ptr(), f.data_ptr() + half, _lib.ptr(wt),
+                                             _lib.dtype_code(f), n, c, h * w, eps, _lib.stream())
+        _lib.check(rc, "gg_feature_distance_forward")
+        ctx.save_for_backward(f, wt)
+        ctx.eps = eps
+        return out.reshape(n, 1, 1, 1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        f, wt = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        n2, c, h, w = f.shape
+        n = n2 // 2
+        g = g.reshape(n).float().contiguous()
+        gf = torch.empty_like(f)
+        half = n * c * h * w * f.element_size()
+        rc = _lib.load().gg_feature_distance_backward(gf.data_ptr(), gf.data_ptr() + half, g.data_ptr(), f.data_ptr(),
+                                                      f.data_ptr() + half, _lib.ptr(wt), _lib.dtype_code(f), n, c, h * w, ctx.eps,
+                                                      _lib.stream())
+        _lib.check(rc, "gg_feature_distance_backward")
+        return gf, None, None
+
+
+def feature_distance_stacked(f, weight=None, eps=1e-10):
+    """feature_distance(f[:N], f[N:], weight) for a stacked (2N, C, H, W) map -> (N, 1, 1, 1)."""
+    _lib.require_cuda(f, weight)
+    if f.dim() != 4 or f.shape[0] % 2 != 0:
+        raise RuntimeError("feature_distance_stacked: expected a (2N, C, H, W) map, got %s" % (tuple(f.shape),))
+    if not _channels_ok(f.shape[1]):
+        raise RuntimeError("feature_distance_stacked: C=%d is not supported by the fused kernel" % f.shape[1])
+    if weight is not None and weight.requires_grad:
+        raise RuntimeError("feature_distance_stacked: trainable `lins` weights are not supported")
+    return _FeatureDistanceStacked.apply(_as_kernel_input(f), weight, float(eps))
+

@@ -43,6 +43,7 @@ def cuda_ops():
             splat2d_lookup=_splat2d_lookup,               # uncongeal_points' grid lookup fused into the splat
             nn_argmin=_nn_argmin,                         # congeal_points' brute-force search without the distance tensor
             feature_distance=_fd.feature_distance,
+            feature_distance_stacked=_fd.feature_distance_stacked,   # both images' features from ONE backbone pass
             bias_relu_pool=_vp.bias_relu_pool,            # VGG slice boundary: bias + ReLU + 2x2 max-pool, one pass each way
             bias_relu_pool_supported=_vp.supported,
         )

@@ -167,6 +167,16 @@ class PerceptualLoss(nn.Module):
             from ..opset import cuda_ops
             ops = cuda_ops()
         native = ops if getattr(ops, "name", None) == "sm_100a" else None
+        if native is not None and in0.is_cuda and in0.shape == in1.shape and hasattr(ops, "feature_distance_stacked"):
+            # ONE backbone pass over both images stacked along the batch (the reference runs the VGG twice, lpips.py:188):
+            # half the launches, larger convolutions; the distance kernel reads the two halves of each stacked map and
+            # writes both gradients into one stacked tensor
+            feats = self.net(self.scaling_layer(torch.cat([in0, in1], 0)).to(dt).contiguous(memory_format=cl), native)
+            val = 0
+            for k, f in enumerate(feats):
+                w = self.lins[k].model[-1].weight.reshape(-1) if self.lpips else None
+                val = val + ops.feature_distance_stacked(f, w)
+            return val / self.divisor
         f0 = self.net(self.scaling_layer(in0).to(dt).contiguous(memory_format=cl), native)
         f1 = self.net(self.scaling_layer(in1).to(dt).contiguous(memory_format=cl), native)
         val = 0

@@ -207,3 +207,42 @@ def test_bias_relu_pool_argument_checks():
         bias_relu_pool(x, None)
     with pytest.raises(RuntimeError):
         bias_relu_pool(torch.randn(1, 64, 4, 4), None)      # no CPU path
+
+
+@pytest.mark.gpu
+def test_stacked_feature_distance_matches_reference_fixture():
+    """feature_distance_stacked(cat(f0, f1)) -- both images' features from ONE backbone pass -- against the reference-generated
+    fixture: value and the gradient of BOTH halves, written into one stacked tensor."""
+    from gangealing_b200.op.feature_distance import feature_distance_stacked
+    blob = load_golden("perceptual")
+    for name in golden_cases(blob):
+        f0, f1, w, out, gout, g0, g1 = _case(blob, name)
+        f = torch.cat([f0, f1], 0).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        res = feature_distance_stacked(f, None if w is None else w.to(DEV))
+        assert_close(res, out, rtol=1e-5, what=name + " out")
+        (gf,) = torch.autograd.grad(res, [f], gout.to(DEV))
+        n = f0.shape[0]
+        assert_close(gf[:n], g0, rtol=1e-4, what=name + " g0")
+        assert_close(gf[n:], g1, rtol=1e-4, what=name + " g1")
+
+
+@pytest.mark.gpu
+def test_whole_perceptual_loss_on_the_gpu_matches_the_reference_lpips_fixture():
+    """The product path of the perceptual loss (one stacked VGG16 pass on cuDNN, fused bias+ReLU(+pool) passes, stacked distance
+    kernel) against the reference LPIPS class run on the CPU with the same seeded weights: value and both input gradients."""
+    from gangealing_b200.training.perceptual import PerceptualLoss
+    from oracle import opset
+    blob = load_golden("perceptual_loss")
+    loss = opset.fill_convs_in_order(PerceptualLoss(), 4242).to(DEV).to(memory_format=torch.channels_last)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        in0 = blob["in0"].to(DEV).requires_grad_(True)
+        in1 = blob["in1"].to(DEV).requires_grad_(True)
+        val = loss(in0, in1) / 1.0
+        assert_close(val, blob["val"], rtol=1e-4, what="loss value")
+        g0, g1 = torch.autograd.grad(val.sum(), [in0, in1])
+        assert_close(g0, blob["g0"], rtol=2e-4, what="gradient wrt image 0")
+        assert_close(g1, blob["g1"], rtol=2e-4, what="gradient wrt image 1")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
