@@ -333,7 +333,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
 //           (the NEXT modulated convolution's input: its style modulation rides in this epilogue, networks.py:236,243)
 //   MODE 2  adjoint epilogue (backward of MODE 1's blur): t = B(in); `out` = t*rs[n,c]; partial[cta][c] = sum t*mul[n,y,x,c]
 //           (the gradient of the demodulation coefficients, <B^T g, raw>, reduced inside the pass that produces B^T g)
-template <typename T, int MODE, bool SEP>
+//   FAST    (MODE 1) the gain-folded epilogue `max(T, T*slope)` is valid for the launch (gain > 0, 0 <= slope <= 1 or linear):
+//           a compile-time variant -- as a run-time flag the compiler predicated BOTH epilogues into the row loop (FSETP /
+//           FSEL / FMUL of the general path: 16 % of the issue slots of the bf16 kernel, which is issue-bound)
+template <typename T, int MODE, bool SEP, bool FAST = false>
 __global__ void __launch_bounds__(kT, 2)
 blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constant__ CUtensorMap tmap,
                  const float* __restrict__ filt, int kh, int kw, const float* __restrict__ noise,
@@ -441,7 +444,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
   }
   // lrelu(t)*gain == max(T, T*slope) with T = gain*t when gain > 0 and 0 <= slope <= 1: the gain is folded into the
   // row scale, the bias and the noise weight, the row scale into the vertical taps (2 epilogue ops per output)
-  const bool fast = FUSED && p.gain > 0.f && ((p.act == 3 && p.alpha >= 0.f && p.alpha <= 1.f) || p.act == 1);
+  constexpr bool fast = FUSED && FAST;    // the host checks gain > 0 && ((act == 3 && 0 <= alpha <= 1) || act == 1)
   const float neg = (p.act == 3) ? p.alpha : 1.f;
   if (fast) {
 #pragma unroll
@@ -449,6 +452,11 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
     nw *= p.gain;
   }
   const int xo = x_out0 + COLS * xg;      // first of this thread's output columns
+  // element offset of this thread's first channel at output (n, oy0 + ro, xo): kept as a RUNNING 64-bit value (ro advances
+  // by one per input row) -- recomputing ((n*H + oy)*W + x)*C + c per row and column cost ~30 integer instructions a row
+  const int64_t row_stride = static_cast<int64_t>(p.out_w) * p.c;
+  const int64_t obase = ((static_cast<int64_t>(n) * p.out_h + oy0) * p.out_w + xo) * p.c + c0 + cq * V;   // ro = 0
+  int64_t ocur = obase - 3 * row_stride;                                                                  // ro = r_in - 3
   bool okc[COLS];
 #pragma unroll
   for (int j = 0; j < COLS; ++j) okc[j] = xo + j < p.out_w;
@@ -458,6 +466,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
   for (int rr = 0; rr < kRY; ++rr)
 #pragma unroll
     for (int j = 0; j < COLS; ++j) nzn[rr][j] = 0.f;
+  const float* noise_base = noise ? noise + (static_cast<int64_t>(n) * p.out_h + oy0) * p.out_w + xo : nullptr;   // row ro = 0
   auto fetch_noise = [&](int it_) {
 #pragma unroll
     for (int rr = 0; rr < kRY; ++rr) {
@@ -465,7 +474,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
 #pragma unroll
       for (int j = 0; j < COLS; ++j) nzn[rr][j] = 0.f;
       if (ro >= 0 && ro < rows_out) {
-        const float* np_ = noise + (static_cast<int64_t>(n) * p.out_h + oy0 + ro) * p.out_w + xo;
+        const float* np_ = noise_base + static_cast<int64_t>(ro) * p.out_w;
 #pragma unroll
         for (int j = 0; j < COLS; ++j)
           if (okc[j]) nzn[rr][j] = __ldg(np_ + j);
@@ -481,7 +490,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
   for (int j = 0; j < COLS; ++j) mcur[j] = mnext[j] = make_uint4(0u, 0u, 0u, 0u);
   auto fetch_mul = [&](int ro_) {
     if (ro_ >= 0 && ro_ < rows_out) {
-      const int64_t mo = (((static_cast<int64_t>(n) * p.out_h + oy0 + ro_) * p.out_w + xo) * p.c + c0) + cq * V;
+      const int64_t mo = obase + ro_ * row_stride;
 #pragma unroll
       for (int j = 0; j < COLS; ++j)
         if (okc[j]) mnext[j] = __ldg(reinterpret_cast<const uint4*>(mul + mo + static_cast<int64_t>(j) * p.c));
@@ -517,7 +526,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
       for (int rr = 0; rr < kRY; ++rr) {
         const int ro = (it + 1) * kRY + rr - 3;
         if (ro >= 0 && ro < rows_out) {
-          const T* mp = mul + (((static_cast<int64_t>(n) * p.out_h + oy0 + ro) * p.out_w + xo) * p.c + c0) + cq * V;
+          const T* mp = mul + obase + ro * row_stride;
 #pragma unroll
           for (int j = 0; j < COLS; ++j)
             if (okc[j]) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + static_cast<int64_t>(j) * p.c));
@@ -527,7 +536,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
     mbar_wait(&full_bar[stage], static_cast<uint32_t>((it / kNS) & 1));
     const T* st = tiles + stage * G::STAGE_ELEMS;
 #pragma unroll
-    for (int rr = 0; rr < kRY; ++rr, ++r_in) {
+    for (int rr = 0; rr < kRY; ++rr, ++r_in, ocur += row_stride) {
       if (MODE == 2 && mul) {
 #pragma unroll
         for (int j = 0; j < COLS; ++j) mcur[j] = mnext[j];
@@ -558,7 +567,6 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
       }
       const int ro = r_in - 3;             // output row (relative to oy0) completed by this input row
       if (ro >= 0 && ro < rows_out) {
-        const int oy = oy0 + ro;
 #pragma unroll
         for (int j = 0; j < COLS; ++j) {
           float a4[V];
@@ -581,7 +589,7 @@ blur_nhwc_kernel(T* __restrict__ out, T* __restrict__ out2, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < V; ++k) a4[k] = fmaf(kf[a][b], rwin[(rr + 1 + a) & 3][j + b][k], a4[k]);
           }
-          const int64_t ooff = (((static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + xo + j) * p.c + c0) + cq * V;
+          const int64_t ooff = ocur + j * p.c;
           if (FUSED) {
             const float nzj = nw * nzc[rr][j];
             float o2[V];
@@ -909,26 +917,32 @@ static int launch_blur(void* out, void* out2, const void* in, const float* kerne
   static DeviceOnce configured;
   if (configured.needed()) {
     cudaError_t e = cudaSuccess;
-    const void* kernels[6] = {reinterpret_cast<const void*>(blur_nhwc_kernel<T, 0, true>),
+    const void* kernels[8] = {reinterpret_cast<const void*>(blur_nhwc_kernel<T, 0, true>),
                               reinterpret_cast<const void*>(blur_nhwc_kernel<T, 0, false>),
-                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, true>),
-                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, false>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, true, false>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, false, false>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, true, true>),
+                              reinterpret_cast<const void*>(blur_nhwc_kernel<T, 1, false, true>),
                               reinterpret_cast<const void*>(blur_nhwc_kernel<T, 2, true>),
                               reinterpret_cast<const void*>(blur_nhwc_kernel<T, 2, false>)};
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_fail(e, "blur_nhwc smem opt-in");
     configured.done();
   }
   auto st = static_cast<cudaStream_t>(stream);
   float* partial = (mode == 2 && row_dot) ? static_cast<float*>(workspace) : nullptr;
-#define GG_BLUR(M_, S_)                                                                                              \
-  blur_nhwc_kernel<T, M_, S_><<<grid, kT, smem, st>>>(static_cast<T*>(out), static_cast<T*>(out2), tmap, kernel, kernel_h,  \
-                                                     kernel_w, noise, noise_weight, bias, row_scale, scale2,         \
-                                                     static_cast<const T*>(mul), partial, p)
-  if (mode == 1) { if (separable) GG_BLUR(1, true); else GG_BLUR(1, false); }
-  else if (mode == 2) { if (separable) GG_BLUR(2, true); else GG_BLUR(2, false); }
-  else { if (separable) GG_BLUR(0, true); else GG_BLUR(0, false); }
+  const bool fast = scale > 0.f && ((act == 3 && alpha >= 0.f && alpha <= 1.f) || act == 1);
+#define GG_BLUR(M_, S_, F_)                                                                                          \
+  blur_nhwc_kernel<T, M_, S_, F_><<<grid, kT, smem, st>>>(static_cast<T*>(out), static_cast<T*>(out2), tmap, kernel, kernel_h, \
+                                                         kernel_w, noise, noise_weight, bias, row_scale, scale2,     \
+                                                         static_cast<const T*>(mul), partial, p)
+  if (mode == 1) {
+    if (fast) { if (separable) GG_BLUR(1, true, true); else GG_BLUR(1, false, true); }
+    else { if (separable) GG_BLUR(1, true, false); else GG_BLUR(1, false, false); }
+  }
+  else if (mode == 2) { if (separable) GG_BLUR(2, true, false); else GG_BLUR(2, false, false); }
+  else { if (separable) GG_BLUR(0, true, false); else GG_BLUR(0, false, false); }
 #undef GG_BLUR
   GG_CHECK_LAUNCH("blur_nhwc launch");
   if (partial) {

@@ -44,7 +44,9 @@ struct TailFwdParams {
 // CTA = `chunk` consecutive pixels of one sample.  The per-channel constants of that sample (demod*gain, bias*gain, s_next,
 // the three to-RGB rows) are staged once in shared memory; a group of 8 lanes owns 4 consecutive pixels per trip and walks
 // the channel vectors v = lane + 8j: 4 independent 16-byte loads in flight per lane, every constant fetched once per 4 pixels.
-template <typename T>
+// FAST: the gain-folded epilogue max(T, T*slope) is valid for the launch (host check) -- compile-time, so that the general
+// select-and-scale epilogue is not predicated into the pixel loop next to it.
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(kT, 2)
 styled_tail_nhwc_kernel(const TailFwdParams p) {
   constexpr int V = ChanVec<T>::V;
@@ -57,7 +59,7 @@ styled_tail_nhwc_kernel(const TailFwdParams p) {
   const int64_t n = blockIdx.x / p.chunks_per_sample;
   const int ck = blockIdx.x - n * p.chunks_per_sample;
   const int64_t p0 = static_cast<int64_t>(ck) * p.chunk, p1 = min(p0 + p.chunk, p.hw);
-  const bool fast = p.gain > 0.f && ((p.act == 3 && p.alpha >= 0.f && p.alpha <= 1.f) || p.act == 1);
+  constexpr bool fast = FAST;   // gain > 0 && ((act == 3 && 0 <= alpha <= 1) || act == 1)
   const float neg = (p.act == 3) ? p.alpha : 1.f;
   const float gfold = fast ? p.gain : 1.f;   // lrelu(t)*g == max(T, T*slope) with T = g*t: the gain folds into d, b, nw
   for (int c = threadIdx.x; c < C; c += kT) {
@@ -343,8 +345,15 @@ int gg_styled_tail_nhwc(void* out, void* xs, float* rgb, const void* raw, const 
   p.chunk = static_cast<int>(chunk); p.chunks_per_sample = K;
   const size_t smem = static_cast<size_t>(6) * C * sizeof(float);
   auto st = static_cast<cudaStream_t>(stream);
-  if (dtype == GG_F32) styled_tail_nhwc_kernel<float><<<static_cast<unsigned>(grid), kT, smem, st>>>(p);
-  else styled_tail_nhwc_kernel<__nv_bfloat16><<<static_cast<unsigned>(grid), kT, smem, st>>>(p);
+  const bool fast = p.gain > 0.f && ((p.act == 3 && p.alpha >= 0.f && p.alpha <= 1.f) || p.act == 1);
+  const unsigned g = static_cast<unsigned>(grid);
+  if (dtype == GG_F32) {
+    if (fast) styled_tail_nhwc_kernel<float, true><<<g, kT, smem, st>>>(p);
+    else styled_tail_nhwc_kernel<float, false><<<g, kT, smem, st>>>(p);
+  } else {
+    if (fast) styled_tail_nhwc_kernel<__nv_bfloat16, true><<<g, kT, smem, st>>>(p);
+    else styled_tail_nhwc_kernel<__nv_bfloat16, false><<<g, kT, smem, st>>>(p);
+  }
   GG_CHECK_LAUNCH("styled_tail_nhwc launch");
   return GG_OK;
 }
