@@ -77,20 +77,18 @@ class WeightScaler:
         """layers: [(module, scale)] in FORWARD order; module.weight is the fp32 master parameter."""
         self.groups, self.by_module = [], {}
         self.active = False
-        group, size = _Group(), 0
-        for module, scale in layers:
+        for module, _ in layers:
             w = module.weight
             _lib.require_cuda(w)
             if w.dtype != torch.float32 or not (w.is_contiguous() or w.is_contiguous(memory_format=torch.channels_last)):
                 raise RuntimeError("WeightScaler: master weights must be dense fp32 tensors")
-            if size and size + w.numel() * 4 > group_bytes:
-                self.groups.append(group)
-                group, size = _Group(), 0
-            e = _Entry(module, scale, group)
-            group.entries.append(e)
-            self.by_module[module] = e
-            size += w.numel() * 4
-        if group.entries:
+        for members in plan_groups([m.weight.numel() * 4 for m, _ in layers], group_bytes):
+            group = _Group()
+            for i in members:
+                module, scale = layers[i]
+                e = _Entry(module, scale, group)
+                group.entries.append(e)
+                self.by_module[module] = e
             self.groups.append(group)
         self.device = layers[0][0].weight.device if layers else None
 
@@ -157,11 +155,23 @@ class WeightScaler:
                                                        slot["blocks"], _CHUNK, _lib.stream()), "gg_scale_cast_multi")
 
 
+def plan_groups(sizes, group_bytes):
+    """Consecutive layers (forward order) -> groups of at most ~`group_bytes` of parameters; a layer larger than that is a
+    group of its own.  -> list of index lists covering range(len(sizes)) in order."""
+    groups, cur, acc = [], [], 0
+    for i, sz in enumerate(sizes):
+        if cur and acc + sz > group_bytes:
+            groups.append(cur)
+            cur, acc = [], 0
+        cur.append(i)
+        acc += sz
+    if cur:
+        groups.append(cur)
+    return groups
+
+
 def equalized_layers(network):
-    """[(module, scale)] of every EqualConv2d / EqualLinear of `network` in registration (= forward) order."""
-    out = []
-    for m in network.modules():
-        if hasattr(m, "weight") and hasattr(m, "scale") and isinstance(getattr(m, "scale"), float) \
-                and type(m).__name__ in ("EqualConv2d", "EqualLinear") and m.weight.requires_grad:
-            out.append((m, m.scale))
-    return out
+    """[(module, scale)] of every trainable EqualConv2d / EqualLinear of `network` in registration (= forward) order."""
+    from ..stylegan2.networks import EqualConv2d, EqualLinear
+    return [(m, float(m.scale)) for m in network.modules()
+            if isinstance(m, (EqualConv2d, EqualLinear)) and m.weight.requires_grad]

@@ -75,3 +75,28 @@ def test_ops_refuse_cpu_tensors():
         op.fused_leaky_relu(torch.zeros(1, 4, 2, 2), torch.zeros(4))
     with pytest.raises(RuntimeError):
         channel_scale(torch.zeros(1, 4, 2, 2), torch.ones(1, 4))
+
+
+def test_weight_scaler_group_plan_and_layer_discovery():
+    """op/scaled_weights: groups are consecutive runs of layers in forward order, bounded by a byte budget (an oversized layer
+    stands alone), and the layer discovery finds exactly the trainable EqualConv2d / EqualLinear of a network."""
+    from gangealing_b200.op.scaled_weights import equalized_layers, plan_groups
+    from gangealing_b200.stn import get_stn
+    from oracle import opset
+    assert plan_groups([], 100) == []
+    assert plan_groups([10, 20, 30], 100) == [[0, 1, 2]]
+    assert plan_groups([60, 50, 10, 200, 5, 5], 100) == [[0], [1, 2], [3], [4, 5]]
+    groups = plan_groups([7] * 25, 20)
+    assert [i for g in groups for i in g] == list(range(25)) and all(len(g) <= 2 for g in groups)
+    stn = get_stn(["similarity", "flow"], flow_size=64, supersize=64, channel_multiplier=0.25, num_heads=1, ops=opset.cpu_ops())
+    layers = equalized_layers(stn)
+    names = {id(m): n for n, m in stn.named_modules()}
+    found = [names[id(m)] for m, _ in layers]
+    assert len(found) == len(set(found)) >= 30
+    assert any(n.endswith("final_linear") for n in found) and any("flow_out" in n for n in found) and any(".skip." in n for n in found)
+    assert all(isinstance(s, float) and s > 0 for _, s in layers)
+    # module registration order is the order the layers run in (groups must be runs of consecutively executed layers)
+    assert found.index("stns.0.convs.0.0") < found.index("stns.0.final_conv.0") < found.index("stns.1.convs.0.0")
+    for prm in stn.stns[0].parameters():
+        prm.requires_grad = False
+    assert all(names[id(m)].startswith("stns.1.") for m, _ in equalized_layers(stn))
