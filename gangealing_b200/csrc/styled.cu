@@ -80,25 +80,31 @@ styled_tail_nhwc_kernel(const TailFwdParams p) {
   const int c4_plane = C / 4;                           // float4s per constant plane
   const int l = threadIdx.x & (kGroup - 1), grp = threadIdx.x / kGroup;
   const unsigned gmask = 0xffu << (threadIdx.x & 24);    // the groups of one warp may leave the loop at different trips
-  const T* raw = static_cast<const T*>(p.raw);
-  T* out = static_cast<T*>(p.out);
-  T* xs = static_cast<T*>(p.xs);
-  constexpr int64_t kStride = (kT / kGroup) * kPix;
+  // per-sample base pointers + 32-bit in-sample offsets (the host checks hw*C < 2^31): the pixel loop then needs no 64-bit
+  // multiplies and half the index registers (the bf16 instantiation sits at the 128-register cap of 2 CTAs/SM)
+  const int hw = static_cast<int>(p.hw);
+  const T* raw = static_cast<const T*>(p.raw) + n * hw * C;
+  T* out = p.out ? static_cast<T*>(p.out) + n * hw * C : nullptr;
+  T* xs = p.xs ? static_cast<T*>(p.xs) + n * hw * C : nullptr;
+  const float* noise_n = p.noise ? p.noise + n * hw : nullptr;
+  const int q0 = static_cast<int>(p0), q1 = static_cast<int>(p1);
+  constexpr int kStride = (kT / kGroup) * kPix;
   // software pipeline over (trip, j): the 4 loads of step i+1 are issued before the arithmetic of step i
-  auto pixel = [&](int64_t pb_, int u) { return n * p.hw + min(pb_ + u, p1 - 1); };   // clamped: a tail pixel is recomputed, never stored
+  auto pixel = [&](int pb_, int u) { return min(pb_ + u, q1 - 1); };   // clamped: a tail pixel is recomputed, never stored
   uint4 xn[kPix];
-  int64_t pb = p0 + grp * kPix;
-  if (pb < p1) {
+  int pb = q0 + grp * kPix;
+  if (pb < q1) {
 #pragma unroll
-    for (int u = 0; u < kPix; ++u) xn[u] = ldg_stream16(raw + (pixel(pb, u) * nvec + l) * V);
+    for (int u = 0; u < kPix; ++u) xn[u] = ldg_stream16(raw + static_cast<unsigned>(pixel(pb, u) * C + l * V));
   }
-  for (; pb < p1; pb += kStride) {
+  for (; pb < q1; pb += kStride) {
     float nz[kPix];
-    int64_t pix[kPix];
+    unsigned po[kPix];                // element offset of the pixel's channel 0 inside the sample
 #pragma unroll
     for (int u = 0; u < kPix; ++u) {
-      pix[u] = pixel(pb, u);
-      nz[u] = p.noise ? nw * __ldg(p.noise + pix[u]) : 0.f;
+      const int px = pixel(pb, u);
+      po[u] = static_cast<unsigned>(px) * static_cast<unsigned>(C);
+      nz[u] = noise_n ? nw * __ldg(noise_n + px) : 0.f;
     }
     float acc[kPix][3];
 #pragma unroll
@@ -110,11 +116,11 @@ styled_tail_nhwc_kernel(const TailFwdParams p) {
       for (int u = 0; u < kPix; ++u) xr[u] = xn[u];
       {  // prefetch the next step: (pb, j+1) or (pb + stride, 0)
         const bool wrap = (j + 1 == J);
-        const int64_t pbn = wrap ? pb + kStride : pb;
+        const int pbn = wrap ? pb + kStride : pb;
         const int vn = wrap ? l : v + kGroup;
-        if (pbn < p1) {
+        if (pbn < q1) {
 #pragma unroll
-          for (int u = 0; u < kPix; ++u) xn[u] = ldg_stream16(raw + (pixel(pbn, u) * nvec + vn) * V);
+          for (int u = 0; u < kPix; ++u) xn[u] = ldg_stream16(raw + static_cast<unsigned>(pixel(pbn, u) * C + vn * V));
         }
       }
       float d[V], b[V], s[V], w0[V], w1[V], w2[V];
@@ -150,8 +156,8 @@ styled_tail_nhwc_kernel(const TailFwdParams p) {
             acc[u][2] = fmaf(w2[k], o[k], acc[u][2]);
           }
         }
-        if (pb + u < p1) {
-          const int64_t off = (pix[u] * nvec + v) * V;
+        if (pb + u < q1) {
+          const unsigned off = po[u] + static_cast<unsigned>(v * V);
           if (out) stg_stream16(out + off, ChanVec<T>::pack(o));
           if (xs) stg_stream16(xs + off, ChanVec<T>::pack(o2));
         }
@@ -170,7 +176,7 @@ styled_tail_nhwc_kernel(const TailFwdParams p) {
         const int64_t off = (n * 3 + o) * p.hw + pb;
 #pragma unroll
         for (int u = 0; u < kPix; ++u)
-          if (pb + u < p1) {
+          if (pb + u < q1) {
             const float r = (o == 0 ? acc[u][0] : o == 1 ? acc[u][1] : acc[u][2]) + rb;
             p.rgb[off + u] = r + (p.skip ? __ldg(p.skip + off + u) : 0.f);
           }
@@ -334,7 +340,7 @@ int gg_styled_tail_nhwc(void* out, void* xs, float* rgb, const void* raw, const 
   if (xs && !s_next) return fail(GG_ERR_BAD_ARG, "styled_tail_nhwc: xs needs s_next");
   if (rgb && !wm) return fail(GG_ERR_BAD_ARG, "styled_tail_nhwc: rgb needs wm");
   const int64_t chunk = fwd_chunk(N, HW);
-  if (chunk > 0x7fffff00LL) return fail(GG_ERR_BAD_ARG, "styled_tail_nhwc: plane too large");
+  if (chunk > 0x7fffff00LL || HW * C >= 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "styled_tail_nhwc: plane too large (H*W*C must be < 2^31)");
   const int K = static_cast<int>((HW + chunk - 1) / chunk);
   const int64_t grid = N * K;
   if (grid > 0x7fffffffLL) return fail(GG_ERR_BAD_ARG, "styled_tail_nhwc: too many CTAs");
