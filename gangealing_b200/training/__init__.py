@@ -5,3 +5,4 @@ from .losses import (assign_fake_images_to_clusters, flow_identity_loss, gangeal
 from .latent_learner import DirectionInterpolator
 from .perceptual import PerceptualLoss, get_perceptual_loss
 from .step import TrainConfig, Trainer, accumulate, requires_grad
+from .classifier_step import ClassifierTrainer

@@ -432,8 +432,96 @@ def gen_perceptual_loss(ref_models):
     _save("perceptual_loss", in0=in0.detach(), in1=in1.detach(), val=val.detach(), g0=g0, g1=g1)
 
 
+def classifier_setup(mods, heads=2, flips=True):
+    """The models of one cluster-classifier iteration (shrunk config 5), built from the module classes in `mods` (the
+    reference's here, this repo's in tests/test_classifier_cpu.py) with the same seeded weights."""
+    from oracle import opset
+    gen_size, clusters = 128, heads * (1 + int(flips))
+    g = opset.fill_parameters(mods["Generator"](gen_size, 512, 2, channel_multiplier=1).eval(), 41)
+    stn = mods["get_stn"](["similarity", "flow"], flow_size=64, supersize=gen_size, channel_multiplier=0.25, num_heads=heads)
+    opset.fill_parameters(stn, 42, gain=0.2)
+    ll = mods["DirectionInterpolator"](None, 2, 3, g.n_latent, num_heads=heads)
+    opset.fill_parameters(ll, 43, gain=0.5)
+    cls = mods["ResnetClassifier"](64, channel_multiplier=0.25, num_heads=clusters, supersize=gen_size)
+    opset.fill_parameters(cls, 44, gain=1.0)     # unit gain: logits of order 1, assignments differ between samples
+    resize = mods["BilinearDownsample"](2, 3)
+    for m in (g, stn, ll):
+        for prm in m.parameters():
+            prm.requires_grad = False
+    return g, stn, ll, cls, resize, clusters
+
+
+def classifier_decimate(images):
+    """Image outputs of the run_* helpers are stored as an asymmetric 16x16 sub-grid (a mirrored image lands on other pixels)."""
+    return images[..., ::8, 3::8]
+
+
+def gen_classifier(ref_models):
+    """BASELINE config 5, second half: the reference's ResnetClassifier (models/cluster_classifier.py) -- logits, the
+    run_* inference helpers (exact index outputs), `accuracy` -- and one iteration of train_cluster_classifier.py:84-105
+    (assignments by the frozen clustering STN, cross-entropy, gradients, one Adam step) on CPU with seeded weights."""
+    from torch import nn, optim
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from models import ResnetClassifier, accuracy
+    from models.stylegan2.networks import Generator
+    from models.spatial_transformers.spatial_transformer import get_stn
+    from models.spatial_transformers.antialiased_sampling import BilinearDownsample
+    from models.latent_learner import DirectionInterpolator
+    from models.losses.loss import assign_fake_images_to_clusters
+    mods = dict(Generator=Generator, get_stn=get_stn, DirectionInterpolator=DirectionInterpolator,
+                ResnetClassifier=ResnetClassifier, BilinearDownsample=BilinearDownsample)
+    g, stn, ll, cls, resize, clusters = classifier_setup(mods)
+    out = {}
+    gen = torch.Generator().manual_seed(4400)
+    x = torch.randn(6, 3, 128, 128, generator=gen)          # larger than stn_in_size: goes through input_downsample
+    x = x * torch.linspace(0.3, 2.0, 6).reshape(6, 1, 1, 1) + torch.linspace(-1, 1, 6).reshape(6, 1, 1, 1)
+    dec = classifier_decimate
+    with torch.no_grad():
+        out["cls.x"], out["cls.logits"] = x, cls(x)
+        out["cls.assign"], out["cls.assign_noflip"] = cls.assign(x), cls.assign(x, ignore_flips=True)
+        for c in range(clusters // 2):
+            kept, preds, flip, keep = cls.run(x, c, return_flip_indices=True)
+            out["cls.run%d.kept" % c], out["cls.run%d.preds" % c] = dec(kept), preds
+            out["cls.run%d.flip" % c], out["cls.run%d.keep" % c] = flip, keep
+            flipped, flip_t = cls.run_flip_target(x, c)
+            out["cls.run_flip_target%d.out" % c], out["cls.run_flip_target%d.flip" % c] = dec(flipped), flip_t
+        flipped, preds, classes, flip = cls.run_flip(x)
+        out["cls.run_flip.out"], out["cls.run_flip.classes"], out["cls.run_flip.flip"] = dec(flipped), classes, flip
+        tiled, policy = cls.run_flip_cartesian(x)
+        out["cls.cartesian.out"], out["cls.cartesian.policy"] = dec(tiled), policy
+    pr, gt = torch.randn(16, clusters, generator=gen), torch.randn(16, clusters, generator=gen)
+    out["acc.pred"], out["acc.gt"] = pr, gt
+    out["acc.k1"], out["acc.k2"], out["acc.k3"] = accuracy(pr, gt), accuracy(pr, gt, k=2), accuracy(pr, gt, k=3)
+    # one training iteration, statements of train_cluster_classifier.py:84-105
+    batch, psi = 3, 0.0
+    xent = nn.CrossEntropyLoss()
+    cls_optim = optim.Adam(cls.parameters(), lr=0.001)
+    torch.manual_seed(4321)
+    with torch.no_grad():
+        assigned, _, _, _, resized, distance = assign_fake_images_to_clusters(
+            g, stn, ll, _mse, resize, psi, batch, 512, True, 2, True, "cpu", sample_from_full_res=True, z=None,
+            padding_mode="reflection")
+    predicted = cls(resized[:batch])
+    loss = xent(predicted, assigned.indices)
+    out["step.xent"], out["step.acc1"], out["step.acc2"] = loss.detach(), accuracy(predicted, -distance), accuracy(predicted, -distance, k=2)
+    out["step.assignments"], out["step.distance"], out["step.logits"] = assigned.indices, distance, predicted.detach()
+    out["step.hist_gt"] = torch.bincount(assigned.indices, minlength=clusters).div(float(batch))
+    out["step.hist_pred"] = torch.bincount(predicted.argmax(dim=1), minlength=clusters).div(float(batch))
+    cls.zero_grad()
+    loss.backward()
+    picked = 0
+    for n, prm in cls.named_parameters():
+        if prm.grad is not None and prm.grad.abs().max() > 0 and prm.numel() < 5000 and picked < 6:
+            out["step.grad." + n] = prm.grad.clone()
+            picked += 1
+    cls_optim.step()
+    out["step.after.to_logits.bias"] = cls.to_logits.bias.detach().clone()
+    out["step.after.final_conv.1.bias"] = cls.final_conv[1].bias.detach().clone()
+    _save("classifier", **out)
+
+
 EXTRA_GENERATORS = [gen_mipmap_warp, gen_flow, gen_networks, gen_losses, gen_perceptual, gen_points, gen_stn_options,
-                    gen_perceptual_loss]
+                    gen_perceptual_loss, gen_classifier]
 
 if __name__ == "__main__":
     main()
