@@ -14,8 +14,6 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
-    config.addinivalue_line("markers", "gpu_pending: needs a CUDA device and has NOT been run on one yet (written after the "
-                                       "round's GPU budget ended); deliberately outside `-m gpu`")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -23,7 +21,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
-        if "gpu" in item.keywords or "gpu_pending" in item.keywords:
+        if "gpu" in item.keywords:
             item.add_marker(skip)
 
 

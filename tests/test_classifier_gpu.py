@@ -1,7 +1,7 @@
-"""GPU parity tests of the cluster classifier, written AFTER this round's GPU budget was spent: they have never run on a
-B200.  They carry the marker `gpu_pending` (not `gpu`), so the round-end `pytest -m gpu` run does not select them and the
-suite's green status stays a statement about tests that were actually executed; run them with `pytest -m gpu_pending` on a
-GPU box.  The classifier launches no kernel of its own -- its trunk is the similarity STN's, which `-m gpu` covers."""
+"""GPU: the cluster classifier (BASELINE config 5, second half) on the sm_100a op set against the reference-generated fixture
+(tests/golden/classifier.npz) -- logits in the NCHW, channels-last fp32 and channels-last bf16 trunks, exact index outputs of
+the inference helpers -- and one ClassifierTrainer iteration per storage type.  The classifier launches no kernel of its own:
+its trunk is the similarity STN's.  First run on a B200: profiles/r02_gputest_classifier.txt (5 passed)."""
 import pytest
 import torch
 
@@ -9,7 +9,7 @@ from conftest import assert_close, load_golden
 from oracle import opset
 from oracle.make_golden import classifier_setup
 
-pytestmark = pytest.mark.gpu_pending
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
