@@ -6,7 +6,6 @@ import pytest
 import torch
 
 from conftest import assert_close, load_golden
-from oracle import opset
 from oracle.make_golden import classifier_setup
 
 pytestmark = pytest.mark.gpu

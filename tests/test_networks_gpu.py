@@ -186,7 +186,7 @@ def test_cluster_config5_step_matches_cpu_oracle():
     clustering loss on the GPU op set vs the same host code on the CPU oracle -- loss, EXACT cluster assignments, the
     assigned heads' residual flow and the gradients."""
     from gangealing_b200.training import TrainConfig, Trainer
-    from gangealing_b200.training.losses import assign_fake_images_to_clusters, total_variation_loss
+    from gangealing_b200.training.losses import assign_fake_images_to_clusters
     old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
