@@ -69,6 +69,39 @@ class FusedAdamEMA(torch.optim.Optimizer):
     def lr_tensor(self, group):
         return self._lr[group]
 
+    # ---- checkpoints ---------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        """torch's loader REPLACES every state tensor by a copy of the checkpoint's and hands each parameter its own `step`;
+        the kernel's pointer table (and a captured CUDA graph) holds the addresses of the moment tensors created in
+        `__init__`, and the step count lives in one shared device scalar.  So: load, then copy the loaded values INTO the
+        original tensors (any layout / dtype / device of the checkpoint: the reference's optimisers keep NCHW-strided fp32
+        moments) and put those back -- no address changes, nothing to re-ship, graph replays stay valid."""
+        own = {p: (st["exp_avg"], st["exp_avg_sq"]) for p, st in self.state.items() if "exp_avg" in st}
+        super().load_state_dict(state_dict)
+        steps = []
+        for p, (m, v) in own.items():
+            st = self.state[p]
+            if "exp_avg" in st:
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                steps.append(float(st.get("step", 0.0)))
+            else:                      # a checkpoint taken before the first step has no state for this tensor
+                m.zero_()
+                v.zero_()
+                steps.append(0.0)
+            st["exp_avg"], st["exp_avg_sq"] = m, v
+            st["step"] = self._state3[0:1].view(())
+        if steps and min(steps) != max(steps):
+            raise RuntimeError("FusedAdamEMA.load_state_dict: the checkpoint's tensors disagree on the step count (%g .. %g); "
+                               "the fused step keeps ONE counter for all of them" % (min(steps), max(steps)))
+        self._state3[0:1].fill_(steps[0] if steps else 0.0)
+        for i, g in enumerate(self.param_groups):   # the loaded learning rates go where the kernel reads them
+            lr = g["lr"]
+            if torch.is_tensor(lr):
+                self._lr[i].copy_(lr)
+            elif lr == lr:             # nan marks "set from a device tensor" (set_lr): keep the scalar as it is
+                self._lr[i].fill_(float(lr))
+
     # ---- step ----------------------------------------------------------------------------------------------------
     def _refresh_table(self):
         """Pointer table of this step's tensors.  Gradient tensors are re-created by autograd every iteration (fixed
@@ -105,3 +138,32 @@ class FusedAdamEMA(torch.optim.Optimizer):
                                           self._blocks, _CHUNK, self._state3.data_ptr(), g0["betas"][0], g0["betas"][1], g0["eps"],
                                           self.ema_decay, _lib.stream())
         _lib.check(rc, "gg_adam_ema_step")
+
+
+def split_adam_state_dict(state_dict):
+    """One optimiser `state_dict` with G parameter groups -> G single-group dicts in torch.optim.Adam's layout, parameter
+    indices renumbered from 0: what the reference's checkpoints hold as `t_optim` and `ll_optim` (train.py:20-27)."""
+    out, state = [], state_dict["state"]
+    for group in state_dict["param_groups"]:
+        ids = list(group["params"])
+        g = {k: v for k, v in group.items() if k != "params"}
+        g["params"] = list(range(len(ids)))
+        out.append({"state": {new: state[old] for new, old in enumerate(ids) if old in state}, "param_groups": [g]})
+    return out
+
+
+def merge_adam_state_dicts(state_dicts):
+    """Inverse of `split_adam_state_dict`: the reference's per-network optimiser dicts (each may itself hold several groups)
+    -> one dict whose groups follow each other, parameter indices renumbered consecutively."""
+    state, groups, base = {}, [], 0
+    for sd in state_dicts:
+        count = 0
+        for group in sd["param_groups"]:
+            g = {k: v for k, v in group.items() if k != "params"}
+            g["params"] = [base + i for i in group["params"]]
+            count = max([count] + [i + 1 for i in group["params"]])
+            groups.append(g)
+        for i, st in sd["state"].items():
+            state[base + int(i)] = st
+        base += count
+    return {"state": state, "param_groups": groups}

@@ -217,6 +217,48 @@ class Trainer:
         self.set_schedule(psi=s["psi"], lr=s["stn_lr"], ll_lr=s["ll_lr"])
         return s
 
+    # ---- checkpoints in the reference's layout (train.py:20-27 `save_state_dict`, :214-224 restore) -----------------------
+    def checkpoint(self, iteration=None):
+        """-> dict with the reference's keys: `g_ema`, `t`, `t_ema`, `t_optim`, `ll`, `ll_optim` (optimiser dicts in
+        torch.optim.Adam's layout, whichever optimiser runs here).  The reference's `t_sched` / `ll_sched` entries have no
+        counterpart: the schedule is a closed form of the iteration (training/schedule.py), stored as `iteration`."""
+        if self.fused_optim is not None:
+            from .fused_optim import split_adam_state_dict
+            parts = split_adam_state_dict(self.fused_optim.state_dict())
+            t_sd, ll_sd = parts[0], (parts[1] if len(parts) > 1 else None)
+        else:
+            t_sd, ll_sd = self.t_optim.state_dict(), self.ll_optim.state_dict()
+        return {"g_ema": self.generator.state_dict(), "t": self.t_module.state_dict(), "t_ema": self.t_ema.state_dict(),
+                "t_optim": t_sd, "ll": self.ll_module.state_dict(), "ll_optim": ll_sd, "iteration": iteration}
+
+    def load_checkpoint(self, ckpt, load_G_only=False):
+        """Restore from a reference checkpoint (or one of `checkpoint()`): the generator always, and -- unless `load_G_only`
+        or the checkpoint holds nothing else (train.py:216-225 falls through the same way) -- STN, EMA, latent learner and the
+        Adam state.  In place: parameters, moments and the step counter keep their addresses, so a captured graph stays
+        valid.  -> True when the full training state was restored."""
+        self.generator.load_state_dict(ckpt["g_ema"])
+        if load_G_only or "t" not in ckpt:
+            return False
+        self.t_module.load_state_dict(ckpt["t"])
+        self.t_ema.load_state_dict(ckpt["t_ema"])
+        self.ll_module.load_state_dict(ckpt["ll"])
+        if self.fused_optim is not None:
+            from .fused_optim import merge_adam_state_dicts
+            parts = [ckpt["t_optim"]] + ([ckpt["ll_optim"]] if len(self.fused_optim.param_groups) > 1 else [])
+            self.fused_optim.load_state_dict(merge_adam_state_dicts(parts))
+        else:
+            self.t_optim.load_state_dict(ckpt["t_optim"])
+            if ckpt.get("ll_optim") is not None:
+                self.ll_optim.load_state_dict(ckpt["ll_optim"])
+            for scalar, optimiser in ((self.stn_lr_t, self.t_optim), (self.ll_lr_t, self.ll_optim)):
+                if scalar is not None:      # capturable Adam: the learning rate must stay the device scalar the graph reads
+                    for group in optimiser.param_groups:
+                        scalar.copy_(group["lr"]) if torch.is_tensor(group["lr"]) else scalar.fill_(float(group["lr"]))
+                        group["lr"] = scalar
+        if ckpt.get("iteration") is not None:
+            self.set_iteration(int(ckpt["iteration"]))
+        return True
+
     def step(self, z=None, psi=None, lr=None, ll_lr=None):
         """-> dict of (rank-0 averaged) scalar loss tensors, still on the device (no host sync here).
         After `capture()` the iteration is replayed from a CUDA graph (z, if given, is copied into its static input;
