@@ -65,6 +65,36 @@ class ClassifierTrainer:
                 group["lr"] = lr
         return lr
 
+    def checkpoint(self, iteration=None):
+        """The reference's classifier checkpoint (train_cluster_classifier.py:25-29): `classifier`, `g_ema`, `t_ema`, `ll`,
+        `cls_optim` (torch.optim.Adam's layout; the fused optimiser holds one group here, so its dict already has it)."""
+        t = self.trainer
+        return {"classifier": self.module.state_dict(), "g_ema": t.generator.state_dict(), "t_ema": t.t_ema.state_dict(),
+                "ll": t.ll_module.state_dict(), "cls_optim": self.optim.state_dict(), "iteration": iteration}
+
+    def load_checkpoint(self, ckpt):
+        """Restore what train_cluster_classifier.py:180-204 restores: generator, clustering STN and latent learner always; the
+        classifier and its optimiser when the checkpoint holds them (-> True), else the classifier keeps its initialisation
+        from the similarity STN (-> False)."""
+        t = self.trainer
+        t.generator.load_state_dict(ckpt["g_ema"])
+        t.t_ema.load_state_dict(ckpt["t_ema"])
+        t.ll_module.load_state_dict(ckpt["ll"])
+        if "classifier" not in ckpt:
+            first = t.t_ema.stns[0] if hasattr(t.t_ema, "stns") else t.t_ema
+            self.module.load_state_dict(first.state_dict(), strict=False)
+            return False
+        self.module.load_state_dict(ckpt["classifier"])
+        self.optim.load_state_dict(ckpt["cls_optim"])
+        if self.lr_t is not None and not hasattr(self.optim, "lr_tensor"):
+            # capturable torch Adam: the learning rate must remain THE device scalar (the fused optimiser's loader does this itself)
+            for group in self.optim.param_groups:
+                self.lr_t.copy_(group["lr"]) if torch.is_tensor(group["lr"]) else self.lr_t.fill_(float(group["lr"]))
+                group["lr"] = self.lr_t
+        if ckpt.get("iteration") is not None:
+            self.set_iteration(int(ckpt["iteration"]))
+        return True
+
     def losses(self, z=None):
         t, cfg = self.trainer, self.cfg
         with torch.no_grad():   # image formation and cluster assignment are not differentiated (reference :84-89)

@@ -141,3 +141,29 @@ def test_trainer_checkpoint_round_trip_resumes_identically():
     assert c.load_checkpoint({"g_ema": ckpt["g_ema"]}) is False
     assert all(torch.equal(p, q) for p, q in zip(a.generator.parameters(), c.generator.parameters()))
     assert not all(torch.equal(p, q) for p, q in zip(a.t_module.parameters(), c.t_module.parameters()))
+
+
+def test_classifier_trainer_checkpoint_round_trip():
+    from gangealing_b200.training import ClassifierTrainer, TrainConfig, Trainer
+    cpu = opset.cpu_ops()
+    cfg = TrainConfig(gen_size=64, flow_size=64, dim_latent=16, n_mlp=1, batch=2, inject=3, num_heads=2, flips=True, ndirs=2,
+                      stn_channel_multiplier=0.25, gen_channel_multiplier=1, padding_mode="reflection")
+    a = ClassifierTrainer(Trainer(cfg, "cpu", ops=cpu), ops=cpu)
+    for _ in range(2):
+        a.step()
+    ckpt = copy.deepcopy(a.checkpoint())
+    assert {"classifier", "g_ema", "t_ema", "ll", "cls_optim"} <= set(ckpt)      # train_cluster_classifier.py:25-29
+    b = ClassifierTrainer(Trainer(cfg, "cpu", ops=cpu), ops=cpu)
+    b.step()
+    assert b.load_checkpoint(ckpt) is True
+    z = torch.randn(cfg.batch, cfg.dim_latent)
+    for tr in (a, b):
+        torch.manual_seed(5)
+        out = tr.step(z)
+    assert all(torch.equal(p, q) for p, q in zip(a.module.parameters(), b.module.parameters()))
+    assert torch.isfinite(out["cross_entropy"])
+    # a GANgealing checkpoint without a classifier (the first launch of train_cluster_classifier.py): trunk from the STN
+    c = ClassifierTrainer(Trainer(cfg, "cpu", ops=cpu), ops=cpu, init_from_stn=False)
+    assert c.load_checkpoint({k: ckpt[k] for k in ("g_ema", "t_ema", "ll")}) is False
+    trunk = dict(c.trainer.t_ema.stns[0].named_parameters())
+    assert all(torch.equal(p, trunk[n]) for n, p in c.module.named_parameters() if n.startswith(("convs.", "final_conv.")))
