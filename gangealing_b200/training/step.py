@@ -234,8 +234,13 @@ class Trainer:
     def load_checkpoint(self, ckpt, load_G_only=False):
         """Restore from a reference checkpoint (or one of `checkpoint()`): the generator always, and -- unless `load_G_only`
         or the checkpoint holds nothing else (train.py:216-225 falls through the same way) -- STN, EMA, latent learner and the
-        Adam state.  In place: parameters, moments and the step counter keep their addresses, so a captured graph stays
-        valid.  -> True when the full training state was restored."""
+        Adam state.  In place: parameters, moments and the step counter keep their addresses (the fused kernels' pointer
+        tables stay valid).  A captured CUDA graph is nevertheless RELEASED: the frozen generator's derived filter banks
+        (`scale * W` re-laid out, `sum W^2`: memoised per parameter version, op/modconv.py) are constants of the capture, and
+        a replay would keep synthesising with the old generator -- call `capture()` again.
+        -> True when the full training state was restored."""
+        if self._graph is not None:
+            self.release_graph()
         self.generator.load_state_dict(ckpt["g_ema"])
         if load_G_only or "t" not in ckpt:
             return False
