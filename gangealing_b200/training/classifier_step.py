@@ -77,6 +77,8 @@ class ClassifierTrainer:
         classifier and its optimiser when the checkpoint holds them (-> True), else the classifier keeps its initialisation
         from the similarity STN (-> False)."""
         t = self.trainer
+        if getattr(t, "_graph", None) is not None:    # as Trainer.load_checkpoint: derived generator weights are capture constants
+            t.release_graph()
         t.generator.load_state_dict(ckpt["g_ema"])
         t.t_ema.load_state_dict(ckpt["t_ema"])
         t.ll_module.load_state_dict(ckpt["ll"])
