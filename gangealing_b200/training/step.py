@@ -288,6 +288,7 @@ class Trainer:
         all-reduces and the loss reduce are captured as graph nodes too."""
         if self.distributed:
             warmup = max(warmup, 11)  # DDP needs >= 11 eager iterations on the side stream before capture (PyTorch docs)
+        self.release_graph()          # re-capture: the warm-up below runs eagerly (see the guard in _eager_step)
         cfg = self.cfg
         self._static_z = torch.randn(cfg.batch, cfg.dim_latent, device=self.device)
         side = self._side if self._side is not None else torch.cuda.Stream()
@@ -311,6 +312,11 @@ class Trainer:
         self._static_out = None
 
     def _eager_step(self, z=None):
+        if self._graph is not None:
+            # the captured graph re-reads the pinned pointer tables of the multi-tensor kernels (optimiser, weight scaler) at
+            # every replay; an eager step rewrites those tables with ITS tensors' addresses -- later replays would scatter
+            # into freed memory.  step() never mixes the two; refuse a direct call that would.
+            raise RuntimeError("Trainer: an eager step while a captured graph is held; call release_graph() first")
         cfg = self.cfg
         # the scaled-weight cache is valid for exactly one forward + backward: the optimiser below changes the parameters
         scope = self.weight_scaler.step() if self.weight_scaler is not None else contextlib.nullcontext()

@@ -167,3 +167,16 @@ def test_classifier_trainer_checkpoint_round_trip():
     assert c.load_checkpoint({k: ckpt[k] for k in ("g_ema", "t_ema", "ll")}) is False
     trunk = dict(c.trainer.t_ema.stns[0].named_parameters())
     assert all(torch.equal(p, trunk[n]) for n, p in c.module.named_parameters() if n.startswith(("convs.", "final_conv.")))
+
+
+def test_eager_step_is_refused_while_a_captured_graph_is_held():
+    """The captured graph re-reads the multi-tensor kernels' pinned pointer tables; an eager step would overwrite them."""
+    from gangealing_b200.training import TrainConfig, Trainer
+    cfg = TrainConfig(gen_size=64, flow_size=64, dim_latent=16, n_mlp=1, batch=1, inject=3, stn_channel_multiplier=0.25,
+                      gen_channel_multiplier=1)
+    tr = Trainer(cfg, "cpu", ops=opset.cpu_ops())
+    tr._graph = object()                      # stands in for a torch.cuda.CUDAGraph (none can exist on CPU)
+    with pytest.raises(RuntimeError, match="release_graph"):
+        tr._eager_step()
+    tr.release_graph()
+    assert tr._graph is None and torch.isfinite(tr.step()["p"])
