@@ -116,9 +116,11 @@ def cpu_step_rate(batch, steps=1, warmup=0):
     reference code (oracle/_ref/refpy_cpu, byte-compiled from /root/reference by oracle/build_ref.py) through its own native
     CPU branches (oracle/reference_step.py); kind "port": the oracle port (this repo's host code on the oracle's CPU op
     set) when that tree was not built."""
+    import contextlib
     from oracle import reference_step
     if reference_step.available() and os.environ.get("GG_CPU_KIND", "reference") == "reference":
-        rate, sec, _ = reference_step.step_rate(batch, steps=steps, warmup=warmup, threads=cpu_threads())
+        with contextlib.redirect_stdout(sys.stderr):   # the reference prints ("Loading VGG ..."); stdout carries ONE JSON line
+            rate, sec, _ = reference_step.step_rate(batch, steps=steps, warmup=warmup, threads=cpu_threads())
         return rate, sec, "reference"
     from oracle import opset
     from gangealing_b200.training import TrainConfig, Trainer

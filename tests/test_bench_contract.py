@@ -20,8 +20,8 @@ def test_reference_arm_prints_one_contract_line(kind):
     proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
                            "--warmup", "0", "--cpu-batch", "1"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert proc.returncode == 0, proc.stderr[-2000:]
-    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 1, proc.stdout[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1 and lines[0].startswith("{"), "stdout must carry exactly ONE JSON line:\n" + proc.stdout[-2000:]
     line = json.loads(lines[0])
     baseline = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert line["impl"] == "reference"
